@@ -1,0 +1,147 @@
+/* ============================================================================
+ * maf.h -- C ABI of libmembrane_b200.so
+ *
+ * B200-native (sm_100a) drop-in for ONE function of sahu-lab/MembraneAleFem.jl:
+ *
+ *   r_gl, K_gl = calc_r_K(mesh, xms, cps, time, dt, p; args...)
+ *                                   src/analysis/FiniteElement.jl:75-200
+ *
+ * i.e. the per-Newton-iteration global residual vector and consistent tangent
+ * (area elements :98-138, Neumann boundary elements :151-197) of the Helfrich /
+ * incompressible / viscous / ALE-mesh equations on the quadratic B-spline mesh.
+ * The reference has no FFI for this path; the entry points below are what a
+ * Julia `ccall` shim replacing the body of calc_r_K binds.
+ *
+ * Conventions
+ *  - all functions return 0 on success, nonzero on error; text via maf_last_error.
+ *    No exceptions, aborts or signal handlers cross this boundary.
+ *  - all index arrays are the reference's own: Int64, 1-based, column-major.
+ *  - all floating-point data is FP64 (the reference's ComplexF64 is only its
+ *    differentiation device, FiniteElement.jl:113-122; the tangent here is exact).
+ *  - the library never retains a host pointer past the call that received it.
+ *  - one handle is driven by one host thread at a time (not re-entrant per handle).
+ * ========================================================================== */
+#ifndef MAF_H
+#define MAF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct maf_handle maf_handle;
+
+/* Enum codes are the reference's (src/input/Enums.jl). */
+enum { MAF_STATIC = 1, MAF_EUL = 2, MAF_LAG = 3, MAF_ALEV = 4, MAF_ALEVB = 5 };           /* Motion   :67-73  */
+enum { MAF_F_CAVI = 1, MAF_F_COUE = 2, MAF_F_POIS = 3, MAF_F_PULL = 4, MAF_F_BEND = 5 };  /* Scenario :24-30  */
+enum { MAF_BOTTOM = 1, MAF_RIGHT = 2, MAF_TOP = 3, MAF_LEFT = 4 };                        /* Boundary :89-94  */
+enum { MAF_SHEAR = 1, MAF_STRETCH = 2, MAF_MOMENT = 3 };                                  /* Neumann  :131-135 */
+
+/* Sparsity pattern of K (hard part 1).
+ *  MAF_PATTERN_BLK: union over elements of (active LM rows x active LM cols) minus the dof blocks that are
+ *                   identically zero by the equations ((v,pm) (lambda,pm) (vm,v) (vm,lambda) (pm,lambda) for ALE,
+ *                   (vm,lambda) for EUL). The pattern Julia stores on a generic state is a subset of this one and
+ *                   every extra entry is an exact 0.0.
+ *  MAF_PATTERN_SYM: the full LM x LM union. */
+enum { MAF_PATTERN_BLK = 0, MAF_PATTERN_SYM = 1 };
+
+/* Scatter paths. Both produce the same pattern; DETERMINISTIC sums every nnz slot in ascending element-id
+ * order (bitwise reproducible run to run, same order as the reference with one Julia thread). */
+enum { MAF_SCATTER_ATOMIC = 0, MAF_SCATTER_DETERMINISTIC = 1 };
+
+/* Read-only mesh tables. Replaces what calc_r_K reads from `mesh::Mesh` (src/input/Mesh.jl:48-80). */
+typedef struct {
+  int64_t numel, numnp, ndf, nmdf;     /* Mesh.numel, numnp, ndf, nmdf                                  */
+  int64_t num1el, num2el;              /* element id = e1 + (e2-1)*num1el  (Mesh.jl:582-588)            */
+  const int64_t* IX;                   /* 9 x numel   Mesh.IX  (Mesh.jl:574-593)                        */
+  const int64_t* ID;                   /* ndf x numnp Mesh.ID  (Mesh.jl:276-284), 0 = Dirichlet         */
+  const int64_t* LM;                   /* optional (may be NULL): 9ndf x numel, checked == ID[:,IX]     */
+  int32_t dofs[8];                     /* Mesh.dofs: column of vx vy vz vmx vmy vmz lambda pm, 0=absent */
+  /* 1-D basis tables (LineGpBasisFns, src/input/GpBasisFn.jl:143-202). Every entry of the reference's 2-D
+   * tables (GpBasisFnsζα, :96-112) is ONE product of two entries below, so the 2-D values formed on the
+   * device are bit-identical to mesh.area_gp_fns / mesh.bdry_gp_fns. Layout [uel][gp][10] =
+   * (w, N[3], dN[3], ddN[3]); edge tables [2][10] = ζmin_fns, ζmax_fns (w = 1). uel ids are 1-based. */
+  int64_t nuel1, nuel2;
+  const int64_t* uel_ids1;             /* num1el */
+  const int64_t* uel_ids2;             /* num2el */
+  const double* line1;                 /* nuel1 x 3 x 10 */
+  const double* line2;                 /* nuel2 x 3 x 10 */
+  const double* edge1;                 /* 2 x 10 */
+  const double* edge2;                 /* 2 x 10 */
+  double xi[3];                        /* GaussPointsξ(3).ξs (GaussPoint.jl:116-118), used by the DB term */
+  /* inhomogeneous Neumann conditions, Mesh.inh_neu_bcs in its own order, and Mesh.bdry_elems */
+  int32_t n_neu;
+  const int32_t* neu_bdry;             /* Boundary code per condition */
+  const int32_t* neu_type;             /* Neumann code per condition  */
+  const double* neu_val;
+  const int64_t* bdry_elems[4];        /* indexed by Boundary code - 1; element ids, 1-based */
+  int64_t bdry_count[4];
+} maf_mesh_desc;
+
+/* Scalars calc_r_K reads from `p::Params` (src/input/Params.jl:36-55). */
+typedef struct {
+  int32_t motion;        /* p.motion   */
+  int32_t scenario;      /* p.scenario */
+  double kb, kg, zv, pn; /* p.kb p.kg p.ζv p.pn */
+  double adb, am;        /* p.αdb p.αm */
+  int32_t pattern_mode;  /* MAF_PATTERN_* */
+  int32_t device;        /* CUDA device ordinal; -1 = current device */
+} maf_params;
+
+/* One-time setup: uploads the tables, builds the symbolic CSC pattern and the scatter maps on the device. */
+int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* params);
+int maf_destroy(maf_handle* h);
+
+/* Message for the last failing call on this handle (h may be NULL: last maf_create failure). */
+const char* maf_last_error(const maf_handle* h);
+
+/* Symbolic pattern of K = CSC of a SparseMatrixCSC{Float64,Int64}: colptr (nmdf+1) and rowval (nnz),
+ * 1-based, rows sorted within each column. */
+int maf_nnz(maf_handle* h, int64_t* nnz);
+int maf_pattern(maf_handle* h, int64_t* colptr, int64_t* rowval);
+
+/* The hot path with HOST buffers (what the Julia shim calls once per Newton iteration):
+ *   xms  numnp x 3   column-major   (FiniteElement.jl:77)
+ *   cps  numnp x ndf column-major   (FiniteElement.jl:78)
+ *   r    nmdf            out: r_gl
+ *   nzval nnz            out: K_gl.nzval in the order of maf_pattern
+ *   rnorm2 (optional)    out: sum(r.^2)
+ * bend_tm is args[:bend_tm] (only read for MOMENT conditions, FiniteElement.jl:379). */
+int maf_assemble(maf_handle* h, const double* xms, const double* cps, double time, double dt, double bend_tm,
+                 int scatter_mode, double* r, double* nzval, double* rnorm2);
+
+/* Same, with DEVICE pointers (assembly-only sweeps, device-resident Newton loops). Any of d_r / d_nzval /
+ * d_rnorm2 may be NULL: the handle's own buffers are used (see maf_device_buffers). `stream` is a cudaStream_t
+ * (NULL = the handle's stream). Asynchronous with respect to the host. */
+int maf_assemble_device(maf_handle* h, const double* d_xms, const double* d_cps, double time, double dt,
+                        double bend_tm, int scatter_mode, double* d_r, double* d_nzval, double* d_rnorm2,
+                        void* stream);
+
+/* The handle's device buffers (xms: 3 numnp, cps: ndf numnp, r: nmdf, nzval: nnz, rnorm2: 1). */
+int maf_device_buffers(maf_handle* h, double** d_xms, double** d_cps, double** d_r, double** d_nzval,
+                       double** d_rnorm2);
+/* The handle's stream (cudaStream_t) and a blocking wait on it. */
+int maf_stream(maf_handle* h, void** stream);
+int maf_sync(maf_handle* h);
+
+/* Diagnostics: device-side time of the last maf_assemble (CUDA events on the handle's stream), ms:
+ * out[0] h2d, out[1] zero+area kernel, out[2] boundary kernel, out[3] gather/reduce (deterministic path),
+ * out[4] d2h, out[5] whole call. And the number of kernels this handle has launched so far. */
+int maf_timings(maf_handle* h, double* out6);
+int maf_launch_count(maf_handle* h, int64_t* n);
+
+/* Area-element kernel configuration actually used: out[0] threads per CTA, out[1] elements per CTA,
+ * out[2] dynamic shared memory bytes per CTA, out[3] resident CTAs per SM, out[4] SM count. */
+int maf_kernel_info(maf_handle* h, int64_t* out5);
+
+/* Multi-GPU (one process per GPU): restrict this handle to the elements [el_first, el_last] (1-based, inclusive;
+ * a strip of element rows). Rows of r / entries of nzval that receive contributions from other ranks are the
+ * interface set returned by maf_interface (slot indices into nzval and row indices into r, 1-based); the caller
+ * reduces exactly those with its collective (NCCL). */
+int maf_set_element_range(maf_handle* h, int64_t el_first, int64_t el_last);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAF_H */

@@ -1,0 +1,214 @@
+"""ctypes binding of the C ABI in include/maf.h (libmembrane_b200.so) -- the same calls the Julia `ccall` shim of
+INTEGRATION.md makes. There is no CPU fallback: if the CUDA library is missing or no device is present, every entry
+point raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmembrane_b200.so")
+
+PATTERN_BLK, PATTERN_SYM = 0, 1
+SCATTER_ATOMIC, SCATTER_DETERMINISTIC = 0, 1
+
+_I64P = C.POINTER(C.c_int64)
+_I32P = C.POINTER(C.c_int32)
+_F64P = C.POINTER(C.c_double)
+
+
+class MeshDesc(C.Structure):
+    """maf_mesh_desc"""
+    _fields_ = [("numel", C.c_int64), ("numnp", C.c_int64), ("ndf", C.c_int64), ("nmdf", C.c_int64),
+                ("num1el", C.c_int64), ("num2el", C.c_int64),
+                ("IX", _I64P), ("ID", _I64P), ("LM", _I64P), ("dofs", C.c_int32 * 8),
+                ("nuel1", C.c_int64), ("nuel2", C.c_int64), ("uel_ids1", _I64P), ("uel_ids2", _I64P),
+                ("line1", _F64P), ("line2", _F64P), ("edge1", _F64P), ("edge2", _F64P), ("xi", C.c_double * 3),
+                ("n_neu", C.c_int32), ("neu_bdry", _I32P), ("neu_type", _I32P), ("neu_val", _F64P),
+                ("bdry_elems", _I64P * 4), ("bdry_count", C.c_int64 * 4)]
+
+
+class ParamsC(C.Structure):
+    """maf_params"""
+    _fields_ = [("motion", C.c_int32), ("scenario", C.c_int32), ("kb", C.c_double), ("kg", C.c_double),
+                ("zv", C.c_double), ("pn", C.c_double), ("adb", C.c_double), ("am", C.c_double),
+                ("pattern_mode", C.c_int32), ("device", C.c_int32)]
+
+
+class MafError(RuntimeError):
+    pass
+
+
+_lib = None
+
+EXPORTS = ["maf_create", "maf_destroy", "maf_last_error", "maf_nnz", "maf_pattern", "maf_assemble",
+           "maf_assemble_device", "maf_device_buffers", "maf_stream", "maf_sync", "maf_timings", "maf_launch_count",
+           "maf_kernel_info", "maf_set_element_range"]
+
+
+def load_library(path=None):
+    """Load libmembrane_b200.so and declare the signatures. Raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise MafError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback for the assembly)")
+    L = C.CDLL(path)
+    L.maf_last_error.restype = C.c_char_p
+    L.maf_last_error.argtypes = [C.c_void_p]
+    L.maf_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(MeshDesc), C.POINTER(ParamsC)]
+    L.maf_destroy.argtypes = [C.c_void_p]
+    L.maf_nnz.argtypes = [C.c_void_p, _I64P]
+    L.maf_pattern.argtypes = [C.c_void_p, _I64P, _I64P]
+    L.maf_assemble.argtypes = [C.c_void_p, _F64P, _F64P, C.c_double, C.c_double, C.c_double, C.c_int, _F64P, _F64P,
+                               _F64P]
+    L.maf_assemble_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.maf_device_buffers.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 5
+    L.maf_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.maf_sync.argtypes = [C.c_void_p]
+    L.maf_timings.argtypes = [C.c_void_p, _F64P]
+    L.maf_launch_count.argtypes = [C.c_void_p, _I64P]
+    L.maf_kernel_info.argtypes = [C.c_void_p, _I64P]
+    L.maf_set_element_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    if path == LIB_PATH:
+        _lib = L
+    return L
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def make_mesh_desc(mesh, keep):
+    """Fill a maf_mesh_desc from a host `Mesh` (host/mesh.py). `keep` collects the arrays that must stay alive."""
+    d = MeshDesc()
+    d.numel, d.numnp, d.ndf, d.nmdf = mesh.numel, mesh.numnp, mesh.ndf, mesh.nmdf
+    d.num1el, d.num2el = mesh.num1el, mesh.num2el
+    IX = np.asfortranarray(mesh.IX, dtype=np.int64)
+    ID = np.asfortranarray(mesh.ID, dtype=np.int64)
+    keep += [IX, ID]
+    d.IX, d.ID, d.LM = _ptr(IX, C.c_int64), _ptr(ID, C.c_int64), None
+    d.dofs = (C.c_int32 * 8)(*[int(v) for v in mesh.dofs8()])
+    l1, l2 = mesh.line_gp_fns1, mesh.line_gp_fns2
+    u1 = np.ascontiguousarray(l1.uel_ids, dtype=np.int64)
+    u2 = np.ascontiguousarray(l2.uel_ids, dtype=np.int64)
+    t1 = np.ascontiguousarray(l1.ufns, dtype=np.float64)
+    t2 = np.ascontiguousarray(l2.ufns, dtype=np.float64)
+    e1 = np.ascontiguousarray(l1.edge, dtype=np.float64)
+    e2 = np.ascontiguousarray(l2.edge, dtype=np.float64)
+    keep += [u1, u2, t1, t2, e1, e2]
+    d.nuel1, d.nuel2 = t1.shape[0], t2.shape[0]
+    d.uel_ids1, d.uel_ids2 = _ptr(u1, C.c_int64), _ptr(u2, C.c_int64)
+    d.line1, d.line2, d.edge1, d.edge2 = (_ptr(t1, C.c_double), _ptr(t2, C.c_double), _ptr(e1, C.c_double),
+                                          _ptr(e2, C.c_double))
+    from .host.basis import GaussPointsXi
+    d.xi = (C.c_double * 3)(*GaussPointsXi(3).xs.tolist())
+    nb = np.array([int(b) for (b, _, _) in mesh.inh_neu_bcs], dtype=np.int32)
+    nt = np.array([int(t) for (_, t, _) in mesh.inh_neu_bcs], dtype=np.int32)
+    nv = np.array([float(v) for (_, _, v) in mesh.inh_neu_bcs], dtype=np.float64)
+    keep += [nb, nt, nv]
+    d.n_neu = len(nb)
+    d.neu_bdry, d.neu_type, d.neu_val = _ptr(nb, C.c_int32), _ptr(nt, C.c_int32), _ptr(nv, C.c_double)
+    for b in range(1, 5):
+        arr = np.ascontiguousarray(mesh.bdry_elems[b], dtype=np.int64)
+        keep.append(arr)
+        d.bdry_elems[b - 1] = _ptr(arr, C.c_int64)
+        d.bdry_count[b - 1] = len(arr)
+    return d
+
+
+class Assembler:
+    """Owner of one maf_handle: the device-resident replacement of the reference's calc_r_K for one (mesh, Params)."""
+
+    def __init__(self, mesh, p, pattern_mode=PATTERN_BLK, device=-1, lib=None):
+        self.L = lib or load_library()
+        self.mesh, self.p = mesh, p
+        keep = []
+        desc = make_mesh_desc(mesh, keep)
+        par = ParamsC(int(p.motion), int(p.scenario), p.kb, p.kg, p.zv, p.pn, p.adb, p.am, pattern_mode, device)
+        h = C.c_void_p()
+        rc = self.L.maf_create(C.byref(h), C.byref(desc), C.byref(par))
+        if rc != 0:
+            raise MafError(f"maf_create failed ({rc}): {self.L.maf_last_error(None).decode()}")
+        self.h = h
+        n = C.c_int64()
+        self._check(self.L.maf_nnz(self.h, C.byref(n)))
+        self.nnz = n.value
+        self.nmdf = mesh.nmdf
+        self._pattern = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MafError(f"libmembrane_b200 error {rc}: {self.L.maf_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.maf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pattern(self):
+        """(colptr, rowval) of K, 1-based Int64 like SparseMatrixCSC."""
+        if self._pattern is None:
+            colptr = np.empty(self.nmdf + 1, dtype=np.int64)
+            rowval = np.empty(self.nnz, dtype=np.int64)
+            self._check(self.L.maf_pattern(self.h, _ptr(colptr, C.c_int64), _ptr(rowval, C.c_int64)))
+            self._pattern = (colptr, rowval)
+        return self._pattern
+
+    def assemble(self, xms, cps, time, dt, bend_tm=1.0, scatter_mode=SCATTER_ATOMIC, r=None, nzval=None):
+        """maf_assemble with host buffers: returns (r, nzval, sum(r^2))."""
+        xms = np.asfortranarray(xms, dtype=np.float64)
+        cps = np.asfortranarray(cps, dtype=np.float64)
+        assert xms.shape == (self.mesh.numnp, 3) and cps.shape == (self.mesh.numnp, self.mesh.ndf)
+        r = np.empty(self.nmdf) if r is None else r
+        nzval = np.empty(self.nnz) if nzval is None else nzval
+        rn = C.c_double()
+        self._check(self.L.maf_assemble(self.h, _ptr(xms, C.c_double), _ptr(cps, C.c_double), time, dt, bend_tm,
+                                        scatter_mode, _ptr(r, C.c_double), _ptr(nzval, C.c_double), C.byref(rn)))
+        return r, nzval, rn.value
+
+    def assemble_device(self, d_xms, d_cps, time, dt, bend_tm=1.0, scatter_mode=SCATTER_ATOMIC, d_r=None,
+                        d_nzval=None, d_rnorm2=None, stream=None):
+        """maf_assemble_device: raw device pointers (ints); None selects the handle's own buffers."""
+        self._check(self.L.maf_assemble_device(self.h, d_xms, d_cps, time, dt, bend_tm, scatter_mode, d_r, d_nzval,
+                                               d_rnorm2, stream))
+
+    def device_buffers(self):
+        ps = [C.c_void_p() for _ in range(5)]
+        self._check(self.L.maf_device_buffers(self.h, *[C.byref(p) for p in ps]))
+        return [p.value for p in ps]
+
+    def stream(self):
+        s = C.c_void_p()
+        self._check(self.L.maf_stream(self.h, C.byref(s)))
+        return s.value
+
+    def sync(self):
+        self._check(self.L.maf_sync(self.h))
+
+    def timings(self):
+        o = np.zeros(6)
+        self._check(self.L.maf_timings(self.h, _ptr(o, C.c_double)))
+        return dict(zip(["h2d_ms", "area_ms", "bdry_ms", "gather_ms", "d2h_ms", "total_ms"], o.tolist()))
+
+    def launch_count(self):
+        n = C.c_int64()
+        self._check(self.L.maf_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def kernel_info(self):
+        o = np.zeros(5, dtype=np.int64)
+        self._check(self.L.maf_kernel_info(self.h, _ptr(o, C.c_int64)))
+        return dict(zip(["threads_per_cta", "elements_per_cta", "smem_bytes", "ctas_per_sm", "sm_count"], o.tolist()))
+
+    def set_element_range(self, el_first, el_last):
+        self._check(self.L.maf_set_element_range(self.h, el_first, el_last))

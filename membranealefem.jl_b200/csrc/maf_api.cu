@@ -1,0 +1,537 @@
+// maf_api.cu -- CUDA kernels (sm_100a) and the C ABI of include/maf.h.
+//
+// Kernels (all FP64 CUDA-core work; the per-element products are 9 x <=6 x <=6 contractions, far too small and too
+// irregular for tcgen05 tiles, and FP64 has no tensor-core advantage on this part -- see DESIGN.md):
+//   area_kernel<MOTION>    persistent CTAs, one area element per CTA iteration: gather -> interpolate ->
+//                          Gauss-point tangent (forward-mode dual numbers) -> residual + factored tangent
+//                          contraction in registers -> scatter (FP64 RED atomics, or staging for the
+//                          deterministic path)
+//   boundary_kernel        one warp per Neumann boundary element
+//   gather_K / gather_r    deterministic path: every nnz slot / residual row sums its staged contributions in
+//                          ascending element order
+//   rnorm2_kernel          sum(r^2), fixed-order two-level reduction
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "maf_host.h"
+
+using namespace maf;
+
+#define MAF_NT 128  // threads per CTA of the area kernel (one element per CTA iteration)
+
+static_assert(sizeof(Config) <= 4000, "Config must fit the kernel parameter space");
+
+// ---------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------
+struct StageSink {      // deterministic path staging buffers (NULL = atomics path)
+  double* kel;          // numel_local x 81 x nij
+  double* rel;          // numel_local x 72
+  const int16_t* task_ij;  // per task: column of the (I,J) class in the staging row
+  int nij;
+};
+
+template <int MOTION>
+__global__ void __launch_bounds__(MAF_NT)
+area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __restrict__ xms,
+            const double* __restrict__ cps, double dt, double* __restrict__ r_gl, double* __restrict__ nzval,
+            const StageSink st, int64_t e0, int64_t e1) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
+  for (int64_t el = e0 + blockIdx.x; el < e1; el += gridDim.x) {
+    phase_gather(tid, MAF_NT, cfg, T, el, xms, cps, sm);
+    __syncthreads();
+    phase_interp(tid, MAF_NT, cfg, sm);
+    __syncthreads();
+    phase_gauss<MOTION>(tid, cfg, dt, sm);
+    __syncthreads();
+    if (st.kel == nullptr) {
+      phase_residual(tid, MAF_NT, cfg, T, el, sm, r_gl, nullptr);
+      KSink sink{nzval, nullptr, nullptr, 0};
+      phase_tangent(tid, cfg, T, el, sm, sink);
+    } else {
+      const int64_t le = el - e0;
+      phase_residual(tid, MAF_NT, cfg, T, el, sm, nullptr, st.rel + 72 * le);
+      KSink sink{nullptr, st.kel + (size_t)81 * st.nij * le, st.task_ij, st.nij};
+      phase_tangent(tid, cfg, T, el, sm, sink);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(128)
+boundary_kernel(const __grid_constant__ Config cfg, const Tables T, const BoundaryTables BT, int bc, double fval,
+                double dt, const double* __restrict__ xms, double* __restrict__ r_gl, double* __restrict__ nzval,
+                int colour, int ncolour, int64_t e0, int64_t e1) {
+  __shared__ double smem[4 * B_DOUBLES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sm = smem + warp * B_DOUBLES;
+  const int n = BT.offs[bc + 1] - BT.offs[bc];
+  // colour < 0: all units concurrently with atomics; otherwise only units k = colour (mod ncolour), plain adds
+  for (int k = blockIdx.x * 4 + warp; k < n; k += gridDim.x * 4) {
+    if (colour >= 0 && (k % ncolour) != colour) continue;
+    const int64_t el = BT.elems[BT.offs[bc] + k];
+    if (el < e0 || el >= e1) continue;
+    boundary_gather(lane, 32, cfg, T, BT, bc, el, xms, sm);
+    __syncwarp();
+    boundary_gauss(lane, 32, cfg, BT, bc, fval, dt, sm);
+    __syncwarp();
+    boundary_scatter(lane, 32, cfg, T, sm, r_gl, nzval, colour >= 0);
+    __syncwarp();
+  }
+}
+
+// Deterministic path (maf_gather.cuh): one thread per node pair / per residual row.
+__global__ void __launch_bounds__(128)
+gather_K_kernel(const __grid_constant__ Config cfg, const Tables T, const GatherTables G,
+                const double* __restrict__ kel, int nij, int64_t e0, int64_t e1, double* __restrict__ nzval) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < G.npairs;
+       p += (int64_t)gridDim.x * blockDim.x)
+    gather_K_pair(p, cfg, T, G, kel, nij, e0, e1, nzval);
+}
+__global__ void __launch_bounds__(128)
+gather_r_kernel(const __grid_constant__ Config cfg, const Tables T, const GatherTables G,
+                const double* __restrict__ rel, int64_t e0, int64_t e1, double* __restrict__ r_gl) {
+  const int64_t n = T.numnp * cfg.ndf;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    gather_r_row(k, cfg, T, G, rel, e0, e1, r_gl);
+}
+
+__global__ void __launch_bounds__(256) rnorm2_partial(const double* __restrict__ r, int64_t n, double* part) {
+  __shared__ double s[256];
+  double acc = 0.0;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    acc += r[k] * r[k];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = s[0];
+}
+__global__ void rnorm2_final(const double* part, int n, double* out) {
+  __shared__ double s[256];
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < n; k += 256) acc += part[k];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = s[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------------
+struct maf_handle {
+  HostModel M;
+  std::string err;
+  int device = 0, sm_count = 0, ctas_per_sm = 0, grid = 0;
+  size_t smem_bytes = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  std::vector<void*> allocs;
+  Tables T{};
+  BoundaryTables BT{};
+  GatherTables G{};
+  bool gather_ready = false;
+  int16_t* d_task_ij = nullptr;
+  int nij = 0;
+  double *d_xms = nullptr, *d_cps = nullptr, *d_r = nullptr, *d_nz = nullptr, *d_rn = nullptr, *d_part = nullptr;
+  double *d_kel = nullptr, *d_rel = nullptr;
+  size_t kel_elems = 0;
+  double *h_pin_in = nullptr, *h_pin_out = nullptr;  // pinned staging for the host-buffer entry point
+  size_t pin_in_bytes = 0, pin_out_bytes = 0;
+  int64_t e0 = 0, e1 = 0;  // element range [e0, e1) assembled by this handle
+  int64_t launches = 0;
+  float ms[6] = {0, 0, 0, 0, 0, 0};
+};
+
+static std::string g_create_err;
+static std::mutex g_mu;
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+
+template <class Tp> static Tp* upload(maf_handle* h, const Tp* src, size_t n) {
+  Tp* d = nullptr;
+  CU(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(Tp)));
+  h->allocs.push_back(d);
+  if (n) CU(cudaMemcpy(d, src, n * sizeof(Tp), cudaMemcpyHostToDevice));
+  return d;
+}
+template <class Tp> static Tp* dalloc(maf_handle* h, size_t n) {
+  Tp* d = nullptr;
+  CU(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(Tp)));
+  h->allocs.push_back(d);
+  return d;
+}
+
+typedef void (*area_fn)(const Config, const Tables, const double*, const double*, double, double*, double*,
+                        const StageSink, int64_t, int64_t);
+static area_fn area_kernel_of(int motion) {
+  switch (motion) {
+    case M_STATIC: return area_kernel<M_STATIC>;
+    case M_EUL: return area_kernel<M_EUL>;
+    case M_LAG: return area_kernel<M_LAG>;
+    case M_ALEV: return area_kernel<M_ALEV>;
+    default: return area_kernel<M_ALEVB>;
+  }
+}
+
+static void ensure_gather(maf_handle* h) {
+  if (h->gather_ready) return;
+  const HostModel& M = h->M;
+  const Symbolic& S = M.sym;
+  GatherHost GH;
+  build_gather_host(M, GH);
+  h->nij = GH.nij;
+  h->G.nbr_ptr = upload(h, S.nbr_ptr.data(), S.nbr_ptr.size());
+  h->G.nbr = upload(h, S.nbr.data(), S.nbr.size());
+  h->G.pair_node = upload(h, GH.pair_node.data(), GH.pair_node.size());
+  h->G.n2e_ptr = upload(h, S.n2e_ptr.data(), S.n2e_ptr.size());
+  h->G.n2e = upload(h, S.n2e.data(), S.n2e.size());
+  h->G.n2e_loc = upload(h, S.n2e_loc.data(), S.n2e_loc.size());
+  h->G.ij_of = upload(h, GH.ij_of.data(), GH.ij_of.size());
+  h->G.npairs = S.npairs;
+  h->d_task_ij = upload(h, GH.task_ij.data(), GH.task_ij.size());
+  h->gather_ready = true;
+}
+
+static void ensure_stage(maf_handle* h) {
+  const size_t ne = (size_t)(h->e1 - h->e0);
+  if (h->d_kel && h->kel_elems >= ne) return;
+  if (h->d_kel) {  // range grew: reallocate
+    cudaFree(h->d_kel);
+    cudaFree(h->d_rel);
+    h->d_kel = h->d_rel = nullptr;
+  }
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  const size_t need = ne * ((size_t)81 * h->nij + 72) * sizeof(double);
+  if (need + ((size_t)1 << 30) > free_b)
+    throw std::runtime_error("deterministic scatter needs " + std::to_string(need >> 20) +
+                             " MiB of staging memory, more than is free on the device");
+  CU(cudaMalloc(&h->d_kel, ne * 81 * h->nij * sizeof(double)));
+  CU(cudaMalloc(&h->d_rel, ne * 72 * sizeof(double)));
+  h->kel_elems = ne;
+}
+
+static void do_assemble_device(maf_handle* h, const double* d_xms, const double* d_cps, double time, double dt,
+                               double bend_tm, int mode, double* d_r, double* d_nz, double* d_rn, cudaStream_t s,
+                               bool timed) {
+  const HostModel& M = h->M;
+  if (!d_r) d_r = h->d_r;
+  if (!d_nz) d_nz = h->d_nz;
+  if (mode != MAF_SCATTER_ATOMIC && mode != MAF_SCATTER_DETERMINISTIC) throw std::runtime_error("unknown scatter mode");
+  if (!(dt == dt) || !(time == time)) throw std::runtime_error("time / dt is NaN");
+  area_fn kern = area_kernel_of(M.motion);
+  const int64_t ne = h->e1 - h->e0;
+  const int grid = (int)std::min<int64_t>(std::max<int64_t>(ne, 1), (int64_t)h->grid);
+  if (timed) CU(cudaEventRecord(h->ev[1], s));
+  StageSink st{nullptr, nullptr, nullptr, 0};
+  if (mode == MAF_SCATTER_ATOMIC) {
+    CU(cudaMemsetAsync(d_r, 0, sizeof(double) * (size_t)M.nmdf, s));
+    CU(cudaMemsetAsync(d_nz, 0, sizeof(double) * (size_t)M.sym.nnz, s));
+  } else {
+    ensure_gather(h);
+    ensure_stage(h);
+    st = StageSink{h->d_kel, h->d_rel, h->d_task_ij, h->nij};
+  }
+  if (ne > 0) {
+    kern<<<grid, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, h->e0, h->e1);
+    CU(cudaGetLastError());
+    h->launches += 1;
+  }
+  if (timed) CU(cudaEventRecord(h->ev[2], s));
+  if (mode == MAF_SCATTER_DETERMINISTIC) {
+    const int gb = h->sm_count * 16;
+    gather_K_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, h->G, h->d_kel, h->nij, h->e0, h->e1, d_nz);
+    CU(cudaGetLastError());
+    gather_r_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, h->G, h->d_rel, h->e0, h->e1, d_r);
+    CU(cudaGetLastError());
+    h->launches += 2;
+  }
+  if (timed) CU(cudaEventRecord(h->ev[3], s));
+  for (int bc = 0; bc < M.n_neu; ++bc) {
+    const int n = M.b_offs[bc + 1] - M.b_offs[bc];
+    if (n == 0) continue;
+    const double fval = neumann_value(M.b_type[bc], M.b_val[bc], time, bend_tm);
+    const int gb = std::min((n + 3) / 4, h->sm_count * 8);
+    if (mode == MAF_SCATTER_ATOMIC) {
+      boundary_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, h->BT, bc, fval, dt, d_xms, d_r, d_nz, -1, 1, h->e0, h->e1);
+      CU(cudaGetLastError());
+      h->launches += 1;
+    } else {
+      // neighbouring boundary elements share two node columns: three colours make concurrent units disjoint
+      for (int c = 0; c < 3; ++c) {
+        boundary_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, h->BT, bc, fval, dt, d_xms, d_r, d_nz, c, 3, h->e0, h->e1);
+        CU(cudaGetLastError());
+        h->launches += 1;
+      }
+    }
+  }
+  if (timed) CU(cudaEventRecord(h->ev[4], s));
+  if (d_rn) {
+    rnorm2_partial<<<256, 256, 0, s>>>(d_r, M.nmdf, h->d_part);
+    rnorm2_final<<<1, 256, 0, s>>>(h->d_part, 256, d_rn);
+    CU(cudaGetLastError());
+    h->launches += 2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+#define MAF_API_BEGIN(h)      \
+  if (!(h)) return 1;         \
+  try {                       \
+    CU(cudaSetDevice((h)->device));
+#define MAF_API_END(h)                  \
+  }                                     \
+  catch (std::exception & e) {          \
+    (h)->err = e.what();                \
+    return 2;                           \
+  }                                     \
+  catch (...) {                         \
+    (h)->err = "unknown error";         \
+    return 3;                           \
+  }                                     \
+  return 0;
+
+extern "C" {
+
+const char* maf_last_error(const maf_handle* h) {
+  if (h) return h->err.c_str();
+  std::lock_guard<std::mutex> lk(g_mu);
+  static thread_local std::string copy;
+  copy = g_create_err;
+  return copy.c_str();
+}
+
+int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* params) {
+  if (!out) return 1;
+  *out = nullptr;
+  maf_handle* h = new (std::nothrow) maf_handle();
+  if (!h) return 1;
+  try {
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+      throw std::runtime_error("no CUDA device: libmembrane_b200 has no CPU fallback for the assembly");
+    if (!params) throw std::runtime_error("null params");
+    int dev = params->device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    if (dev >= ndev) throw std::runtime_error("device ordinal out of range");
+    h->device = dev;
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    h->sm_count = prop.multiProcessorCount;
+
+    build_host_model(h->M, mesh, params, MAF_NT);
+    HostModel& M = h->M;
+    h->e0 = 0;
+    h->e1 = M.numel;
+
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 8; ++k) CU(cudaEventCreate(&h->ev[k]));
+
+    h->T.IX = upload(h, M.IX0.data(), M.IX0.size());
+    h->T.ID = upload(h, M.ID0.data(), M.ID0.size());
+    h->T.nodemask = upload(h, M.sym.nodemask.data(), M.sym.nodemask.size());
+    h->T.uel1 = upload(h, M.uel1.data(), M.uel1.size());
+    h->T.uel2 = upload(h, M.uel2.data(), M.uel2.size());
+    h->T.line1 = upload(h, M.line1.data(), M.line1.size());
+    h->T.line2 = upload(h, M.line2.data(), M.line2.size());
+    h->T.tdb = upload(h, M.tdb.data(), M.tdb.size());
+    h->T.colptr = upload(h, M.sym.colptr.data(), M.sym.colptr.size());
+    h->T.elpair = upload(h, M.sym.elpair.data(), M.sym.elpair.size());
+    h->T.pairoff = upload(h, M.sym.pairoff.data(), M.sym.pairoff.size());
+    h->T.numnp = M.numnp; h->T.numel = M.numel; h->T.num1el = M.num1el; h->T.nuel1 = M.nuel1;
+    h->BT.edge1 = upload(h, M.edge1.data(), M.edge1.size());
+    h->BT.edge2 = upload(h, M.edge2.data(), M.edge2.size());
+    h->BT.elems = upload(h, M.b_elems.data(), M.b_elems.size());
+    h->BT.offs = upload(h, M.b_offs.data(), M.b_offs.size());
+    h->BT.bdry = upload(h, M.b_bdry.data(), M.b_bdry.size());
+    h->BT.ntype = upload(h, M.b_type.data(), M.b_type.size());
+    h->BT.nval = upload(h, M.b_val.data(), M.b_val.size());
+    h->BT.n_neu = M.n_neu;
+    // elpair is only needed on the device from here on; the staging tables of the deterministic path are
+    // uploaded on first use (ensure_gather)
+    h->d_xms = dalloc<double>(h, (size_t)3 * M.numnp);
+    h->d_cps = dalloc<double>(h, (size_t)M.ndf * M.numnp);
+    h->d_r = dalloc<double>(h, (size_t)M.nmdf);
+    h->d_nz = dalloc<double>(h, (size_t)M.sym.nnz);
+    h->d_rn = dalloc<double>(h, 1);
+    h->d_part = dalloc<double>(h, 256);
+    std::vector<int32_t>().swap(M.sym.elpair);
+
+    h->smem_bytes = (size_t)M.cfg.smem_doubles * sizeof(double);
+    area_fn kern = area_kernel_of(M.motion);
+    if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
+      throw std::runtime_error("element needs more shared memory than the device offers");
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    int nb = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, MAF_NT, h->smem_bytes));
+    if (nb < 1) throw std::runtime_error("area kernel does not fit on an SM");
+    h->ctas_per_sm = nb;
+    h->grid = nb * h->sm_count;  // persistent grid: a multiple of the SM count
+  } catch (std::exception& e) {
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      g_create_err = e.what();
+    }
+    maf_destroy(h);
+    return 2;
+  }
+  *out = h;
+  return 0;
+}
+
+int maf_destroy(maf_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->d_kel) cudaFree(h->d_kel);
+  if (h->d_rel) cudaFree(h->d_rel);
+  if (h->h_pin_in) cudaFreeHost(h->h_pin_in);
+  if (h->h_pin_out) cudaFreeHost(h->h_pin_out);
+  for (int k = 0; k < 8; ++k)
+    if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int maf_nnz(maf_handle* h, int64_t* nnz) {
+  MAF_API_BEGIN(h)
+  if (!nnz) throw std::runtime_error("null output pointer");
+  *nnz = h->M.sym.nnz;
+  MAF_API_END(h)
+}
+
+int maf_pattern(maf_handle* h, int64_t* colptr, int64_t* rowval) {
+  MAF_API_BEGIN(h)
+  if (!colptr || !rowval) throw std::runtime_error("null output pointer");
+  const HostModel& M = h->M;
+  for (int64_t c = 0; c <= M.nmdf; ++c) colptr[c] = M.sym.colptr[c] + 1;
+  build_rowval(M.sym, M.ID0.data(), M.cfg.rowmask, rowval);
+  MAF_API_END(h)
+}
+
+int maf_assemble(maf_handle* h, const double* xms, const double* cps, double time, double dt, double bend_tm,
+                 int scatter_mode, double* r, double* nzval, double* rnorm2) {
+  MAF_API_BEGIN(h)
+  if (!xms || !cps || !r || !nzval) throw std::runtime_error("null buffer");
+  const HostModel& M = h->M;
+  cudaStream_t s = h->stream;
+  const size_t bx = sizeof(double) * 3 * (size_t)M.numnp, bc = sizeof(double) * (size_t)M.ndf * M.numnp;
+  const size_t br = sizeof(double) * (size_t)M.nmdf, bk = sizeof(double) * (size_t)M.sym.nnz;
+  // pinned staging keeps the copies asynchronous and at full PCIe rate whatever memory the caller owns
+  if (h->pin_in_bytes < bx + bc) {
+    if (h->h_pin_in) cudaFreeHost(h->h_pin_in);
+    CU(cudaMallocHost(&h->h_pin_in, bx + bc));
+    h->pin_in_bytes = bx + bc;
+  }
+  CU(cudaEventRecord(h->ev[0], s));
+  std::memcpy(h->h_pin_in, xms, bx);
+  std::memcpy((char*)h->h_pin_in + bx, cps, bc);
+  CU(cudaMemcpyAsync(h->d_xms, h->h_pin_in, bx, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(h->d_cps, (char*)h->h_pin_in + bx, bc, cudaMemcpyHostToDevice, s));
+  do_assemble_device(h, h->d_xms, h->d_cps, time, dt, bend_tm, scatter_mode, h->d_r, h->d_nz,
+                     rnorm2 ? h->d_rn : nullptr, s, true);
+  // results straight into the caller's buffers (pageable destinations are staged by the driver)
+  CU(cudaMemcpyAsync(r, h->d_r, br, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(nzval, h->d_nz, bk, cudaMemcpyDeviceToHost, s));
+  if (rnorm2) CU(cudaMemcpyAsync(rnorm2, h->d_rn, sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(h->ev[5], s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]));
+  CU(cudaEventElapsedTime(&h->ms[1], h->ev[1], h->ev[2]));
+  CU(cudaEventElapsedTime(&h->ms[3], h->ev[2], h->ev[3]));
+  CU(cudaEventElapsedTime(&h->ms[2], h->ev[3], h->ev[4]));
+  CU(cudaEventElapsedTime(&h->ms[4], h->ev[4], h->ev[5]));
+  CU(cudaEventElapsedTime(&h->ms[5], h->ev[0], h->ev[5]));
+  MAF_API_END(h)
+}
+
+int maf_assemble_device(maf_handle* h, const double* d_xms, const double* d_cps, double time, double dt,
+                        double bend_tm, int scatter_mode, double* d_r, double* d_nzval, double* d_rnorm2,
+                        void* stream) {
+  MAF_API_BEGIN(h)
+  if (!d_xms || !d_cps) throw std::runtime_error("null device buffer");
+  do_assemble_device(h, d_xms, d_cps, time, dt, bend_tm, scatter_mode, d_r, d_nzval, d_rnorm2,
+                     stream ? (cudaStream_t)stream : h->stream, false);
+  MAF_API_END(h)
+}
+
+int maf_device_buffers(maf_handle* h, double** d_xms, double** d_cps, double** d_r, double** d_nzval,
+                       double** d_rnorm2) {
+  MAF_API_BEGIN(h)
+  if (d_xms) *d_xms = h->d_xms;
+  if (d_cps) *d_cps = h->d_cps;
+  if (d_r) *d_r = h->d_r;
+  if (d_nzval) *d_nzval = h->d_nz;
+  if (d_rnorm2) *d_rnorm2 = h->d_rn;
+  MAF_API_END(h)
+}
+
+int maf_stream(maf_handle* h, void** stream) {
+  MAF_API_BEGIN(h)
+  if (!stream) throw std::runtime_error("null output pointer");
+  *stream = (void*)h->stream;
+  MAF_API_END(h)
+}
+
+int maf_sync(maf_handle* h) {
+  MAF_API_BEGIN(h)
+  CU(cudaStreamSynchronize(h->stream));
+  MAF_API_END(h)
+}
+
+int maf_timings(maf_handle* h, double* out6) {
+  MAF_API_BEGIN(h)
+  if (!out6) throw std::runtime_error("null output pointer");
+  for (int k = 0; k < 6; ++k) out6[k] = h->ms[k];
+  MAF_API_END(h)
+}
+
+int maf_launch_count(maf_handle* h, int64_t* n) {
+  MAF_API_BEGIN(h)
+  if (!n) throw std::runtime_error("null output pointer");
+  *n = h->launches;
+  MAF_API_END(h)
+}
+
+int maf_kernel_info(maf_handle* h, int64_t* out5) {
+  MAF_API_BEGIN(h)
+  if (!out5) throw std::runtime_error("null output pointer");
+  out5[0] = MAF_NT; out5[1] = 1; out5[2] = (int64_t)h->smem_bytes; out5[3] = h->ctas_per_sm; out5[4] = h->sm_count;
+  MAF_API_END(h)
+}
+
+int maf_set_element_range(maf_handle* h, int64_t el_first, int64_t el_last) {
+  MAF_API_BEGIN(h)
+  if (el_first < 1 || el_last > h->M.numel || el_first > el_last + 1)
+    throw std::runtime_error("element range outside 1..numel");
+  h->e0 = el_first - 1;
+  h->e1 = el_last;
+  MAF_API_END(h)
+}
+
+}  // extern "C"

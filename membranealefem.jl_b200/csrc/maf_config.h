@@ -1,0 +1,221 @@
+// maf_config.h -- host-side construction of the element-kernel configuration (block structure of the
+// Gauss-point tangent, work lists, shared-memory layout) from the motion, the dof map and the parameters.
+// Pure C++ (no CUDA) so that the CPU emulation harness in tests/ builds the very same tables.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "maf_element.cuh"
+
+namespace maf {
+
+inline int kind_of(int nr, int nc) {
+  static const int tab[8][2] = {{1, 1}, {1, 2}, {1, 3}, {2, 1}, {2, 2}, {3, 5}, {5, 5}, {6, 5}};
+  for (int k = 0; k < 8; ++k)
+    if (tab[k][0] == nr && tab[k][1] == nc) return k;
+  throw std::runtime_error("no block_accumulate instantiation for this block shape");
+}
+inline int kind_cost(int kind) {
+  static const int tab[8][2] = {{1, 1}, {1, 2}, {1, 3}, {2, 1}, {2, 2}, {3, 5}, {5, 5}, {6, 5}};
+  return 3 * tab[kind][0] * tab[kind][1] + 27 * tab[kind][1];
+}
+
+// dofs8: column (1-based) of vx vy vz vmx vmy vmz lambda pm, or 0 (Mesh.dofs, Bc.jl:414-431)
+inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8], double kb, double kg, double zv,
+                         double pn, double adb, double am, int pattern_sym, int nthreads) {
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.motion = motion;
+  cfg.ndf = ndf;
+  cfg.nthreads = nthreads;
+  cfg.mat = Material{kb, kg, zv, pn, adb, am};
+  cfg.dbscale = adb / zv;
+  cfg.ncomp[F_V] = 3; cfg.ncomp[F_M] = 3; cfg.ncomp[F_L] = 1; cfg.ncomp[F_P] = 1;
+  for (int f = 0; f < NFIELD; ++f)
+    for (int i = 0; i < 3; ++i) cfg.fdof[f][i] = -1;
+  for (int i = 0; i < 3; ++i) { cfg.fdof[F_V][i] = dofs8[i] - 1; cfg.fdof[F_M][i] = dofs8[3 + i] - 1; }
+  cfg.fdof[F_L][0] = dofs8[6] - 1;
+  cfg.fdof[F_P][0] = dofs8[7] - 1;
+  if (cfg.fdof[F_L][0] < 0) throw std::runtime_error("the surface tension must be a degree of freedom");
+  const bool has_m = dofs8[3] || dofs8[4] || dofs8[5];
+  const bool has_p = dofs8[7] != 0;
+  // get_m_motion_order (Mesh.jl:529-542)
+  cfg.mesh_field = motion == M_STATIC ? -1 : (motion == M_LAG ? F_V : F_M);
+  if (motion == M_LAG && has_m) throw std::runtime_error("LAG motion carries no mesh-velocity dofs");
+  if ((motion == M_EUL || motion == M_ALEV || motion == M_ALEVB) && !has_m)
+    throw std::runtime_error("EUL/ALE motion needs mesh-velocity dofs");
+  if ((motion == M_ALEV || motion == M_ALEVB) != has_p)
+    throw std::runtime_error("the mesh pressure is a dof exactly for ALEV/ALEVB");
+
+  const int vr0 = pn != 0.0 ? 0 : 1, vnr = pn != 0.0 ? 6 : 5;
+  struct B { int f, g, c0, nr, d0, nc, db; };
+  std::vector<B> bl;
+  switch (motion) {
+    case M_STATIC:
+      bl = {{F_V, F_V, 1, 2, 1, 2, 0}, {F_V, F_L, 1, 2, 0, 1, 0}, {F_L, F_V, 0, 1, 1, 2, 0}, {F_L, F_L, 0, 1, 0, 1, 1}};
+      break;
+    case M_LAG:
+      bl = {{F_V, F_V, vr0, vnr, 1, 5, 0}, {F_V, F_L, 1, 2, 0, 1, 0}, {F_L, F_V, 0, 1, 1, 2, 0}, {F_L, F_L, 0, 1, 0, 1, 1}};
+      break;
+    case M_EUL:
+      bl = {{F_V, F_V, 1, 2, 1, 2, 0}, {F_V, F_M, vr0, vnr, 1, 5, 0}, {F_V, F_L, 1, 2, 0, 1, 0},
+            {F_M, F_V, 0, 1, 0, 1, 0}, {F_M, F_M, 0, 1, 0, 3, 0},
+            {F_L, F_V, 0, 1, 1, 2, 0}, {F_L, F_M, 0, 1, 1, 2, 0}, {F_L, F_L, 0, 1, 0, 1, 1}};
+      break;
+    case M_ALEV:
+    case M_ALEVB:
+      bl = {{F_V, F_V, 1, 2, 1, 2, 0}, {F_V, F_M, vr0, vnr, 1, 5, 0}, {F_V, F_L, 1, 2, 0, 1, 0},
+            {F_M, F_M, 0, motion == M_ALEVB ? 6 : 3, 1, 5, 0}, {F_M, F_P, 0, 1, 0, 1, 0},
+            {F_L, F_V, 0, 1, 1, 2, 0}, {F_L, F_M, 0, 1, 1, 2, 0}, {F_L, F_L, 0, 1, 0, 1, 1},
+            {F_P, F_V, 0, 1, 0, 1, 0}, {F_P, F_M, 0, 1, 0, 3, 0}, {F_P, F_P, 0, 1, 0, 1, 1}};
+      break;
+    default: throw std::runtime_error("unknown motion code");
+  }
+  // row channel range per field = union over its blocks; column ranges are per block
+  int rlo[NFIELD], rhi[NFIELD];
+  for (int f = 0; f < NFIELD; ++f) { rlo[f] = 99; rhi[f] = -1; }
+  for (int f = 0; f < NFIELD; ++f)
+    for (int g = 0; g < NFIELD; ++g) cfg.coloff[f][g] = -1;
+  for (const B& b : bl) {
+    rlo[b.f] = std::min(rlo[b.f], b.c0);
+    rhi[b.f] = std::max(rhi[b.f], b.c0 + b.nr);
+    cfg.cd0[b.f][b.g] = b.d0;
+    cfg.cnc[b.f][b.g] = b.nc;
+  }
+  int off = 0;
+  for (int f = 0; f < NFIELD; ++f) {
+    if (rhi[f] < 0) { cfg.rc0[f] = 0; cfg.rnc[f] = 0; cfg.aoff[f] = off; cfg.ald[f] = 0; continue; }
+    cfg.rc0[f] = rlo[f];
+    cfg.rnc[f] = rhi[f] - rlo[f];
+    int ld = 0;
+    for (int g = 0; g < NFIELD; ++g)
+      if (cfg.cnc[f][g] > 0) { cfg.coloff[f][g] = ld; ld += cfg.ncomp[g] * cfg.cnc[f][g]; }
+    ld += ld & 1;
+    cfg.ald[f] = ld;
+    cfg.aoff[f] = off;
+    off += cfg.ncomp[f] * cfg.rnc[f] * ld;
+  }
+  cfg.asize = off + (off & 1);
+
+  cfg.nblocks = (int)bl.size();
+  for (int k = 0; k < cfg.nblocks; ++k) {
+    const B& b = bl[k];
+    cfg.blocks[k] = Block{(int8_t)b.f, (int8_t)b.g, (int8_t)b.c0, (int8_t)b.nr, (int8_t)b.d0, (int8_t)b.nc,
+                          (int8_t)kind_of(b.nr, b.nc), (int8_t)b.db};
+  }
+  // tangent tasks, heaviest kinds first so that the lanes of a warp share a code path
+  std::vector<Task> tasks;
+  std::vector<int> order(cfg.nblocks);
+  for (int k = 0; k < cfg.nblocks; ++k) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    return kind_cost(cfg.blocks[x].kind) > kind_cost(cfg.blocks[y].kind);
+  });
+  for (int k : order) {
+    const Block& b = cfg.blocks[k];
+    for (int i = 0; i < cfg.ncomp[b.f]; ++i) {
+      if (cfg.fdof[b.f][i] < 0) continue;
+      for (int j = 0; j < cfg.ncomp[b.g]; ++j) {
+        if (cfg.fdof[b.g][j] < 0) continue;
+        for (int a2 = 0; a2 < 3; ++a2) tasks.push_back(Task{(uint8_t)k, (uint8_t)i, (uint8_t)j, (uint8_t)a2});
+      }
+    }
+  }
+  if ((int)tasks.size() > MAF_MAX_TASKS) throw std::runtime_error("task table overflow");
+  cfg.ntasks = (int)tasks.size();
+  for (int k = 0; k < cfg.ntasks; ++k) cfg.tasks[k] = tasks[k];
+
+  // Gauss-point work items: GEO_A (6 per gp) when the mesh moves, GEO_B (1 per gp), LIN (1 per gp)
+  std::vector<Item> items;
+  if (cfg.mesh_field >= 0) {
+    for (int gp = 0; gp < 9; ++gp)
+      for (int gam = 0; gam < 2; ++gam)
+        for (int j = 0; j < 3; ++j) {
+          if (cfg.fdof[cfg.mesh_field][j] < 0) continue;
+          items.push_back(Item{IT_GEO_A, (uint8_t)gp, (uint8_t)gam, (uint8_t)j});
+        }
+    for (int gp = 0; gp < 9; ++gp) items.push_back(Item{IT_GEO_B, (uint8_t)gp, 0, 0});
+  }
+  for (int gp = 0; gp < 9; ++gp) items.push_back(Item{IT_LIN, (uint8_t)gp, 0, 0});
+  if ((int)items.size() > MAF_MAX_ITEMS) throw std::runtime_error("item table overflow");
+  cfg.nitems = (int)items.size();
+  for (int k = 0; k < cfg.nitems; ++k) cfg.items[k] = items[k];
+
+  // thread -> work maps
+  auto fill = [&](int n, int16_t* slot, int& rounds) {
+    rounds = (n + nthreads - 1) / nthreads;
+    if (rounds * nthreads > MAF_MAX_SLOTS) throw std::runtime_error("slot table overflow");
+    for (int s = 0; s < rounds * nthreads; ++s) slot[s] = (int16_t)(s < n ? s : -1);
+  };
+  fill(cfg.nitems, cfg.item_slot, cfg.item_rounds);
+  fill(cfg.ntasks, cfg.task_slot, cfg.task_rounds);
+
+  // rows present in the pattern of a column of dof J
+  for (int J = 0; J < 8; ++J) cfg.rowmask[J] = 0;
+  for (int g = 0; g < NFIELD; ++g)
+    for (int j = 0; j < cfg.ncomp[g]; ++j) {
+      const int J = cfg.fdof[g][j];
+      if (J < 0) continue;
+      unsigned m = 0;
+      for (int f = 0; f < NFIELD; ++f)
+        for (int i = 0; i < cfg.ncomp[f]; ++i) {
+          if (cfg.fdof[f][i] < 0) continue;
+          if (pattern_sym || cfg.coloff[f][g] >= 0) m |= 1u << cfg.fdof[f][i];
+        }
+      cfg.rowmask[J] = (uint8_t)m;
+    }
+
+  // shared-memory layout (doubles)
+  int o = 0;
+  cfg.o_x = o; o += 27;
+  cfg.o_cv = o; o += 27;
+  cfg.o_cm = o; o += 27;
+  cfg.o_cl = o; o += 9;
+  cfg.o_cp = o; o += 9;
+  cfg.o_w = o; o += 9;
+  cfg.o_phi = o; o += 486;
+  cfg.o_E = o; o += 9 * E_STRIDE;
+  cfg.o_S = o; o += 9 * S_STRIDE;
+  cfg.o_int = o; o += (I_END + 1) / 2;
+  o += o & 1;
+  cfg.o_A = o; o += 9 * cfg.asize;
+  cfg.smem_doubles = o;
+}
+
+// Dohrmann-Bochev matrices tmpDB = G^T H^-1 G of every unique element (FiniteElement.jl:279-281, 315-323):
+// G = sum_gp NDB N^T w, H = sum_gp NDB NDB^T w with NDB = (xi[gp1], xi[gp2], 1). State independent.
+// line tables: [uel][gp][10] = (w, N[3], dN[3], ddN[3]). out: (nuel1*nuel2) x 81, [a][b].
+inline void build_tdb(int nuel1, int nuel2, const double* line1, const double* line2, const double xi[3],
+                      std::vector<double>& out) {
+  out.assign((size_t)nuel1 * nuel2 * 81, 0.0);
+  for (int u2 = 0; u2 < nuel2; ++u2)
+    for (int u1 = 0; u1 < nuel1; ++u1) {
+      double G[3][9] = {{0}}, H[3][3] = {{0}};
+      for (int gp = 0; gp < 9; ++gp) {
+        const double* f1 = line1 + 30 * u1 + 10 * (gp % 3);
+        const double* f2 = line2 + 30 * u2 + 10 * (gp / 3);
+        const double w = f1[0] * f2[0];
+        const double ndb[3] = {xi[gp % 3], xi[gp / 3], 1.0};
+        for (int i = 0; i < 3; ++i) {
+          for (int a = 0; a < 9; ++a) G[i][a] += ndb[i] * (f1[1 + a % 3] * f2[1 + a / 3]) * w;
+          for (int j = 0; j < 3; ++j) H[i][j] += ndb[i] * ndb[j] * w;
+        }
+      }
+      const double a = H[0][0], b = H[0][1], c = H[0][2], d = H[1][0], e = H[1][1], f = H[1][2], g = H[2][0],
+                   h = H[2][1], i = H[2][2];
+      const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+      const double id = 1.0 / det;
+      const double Hi[3][3] = {{(e * i - f * h) * id, (c * h - b * i) * id, (b * f - c * e) * id},
+                               {(f * g - d * i) * id, (a * i - c * g) * id, (c * d - a * f) * id},
+                               {(d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id}};
+      double* T = out.data() + (size_t)81 * (u1 + (size_t)nuel1 * u2);
+      for (int p = 0; p < 9; ++p) {
+        double t1[3];
+        for (int j = 0; j < 3; ++j) t1[j] = G[0][p] * Hi[0][j] + G[1][p] * Hi[1][j] + G[2][p] * Hi[2][j];
+        for (int q = 0; q < 9; ++q) T[9 * p + q] = t1[0] * G[0][q] + t1[1] * G[1][q] + t1[2] * G[2][q];
+      }
+    }
+}
+
+}  // namespace maf

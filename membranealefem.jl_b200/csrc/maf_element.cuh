@@ -1,0 +1,492 @@
+// maf_element.cuh -- one area element of calc_r_K (FiniteElement.jl:98-138) as a sequence of phases that a CTA
+// executes between barriers. Each phase is a __host__ __device__ function of (tid, nthreads, shared-memory block),
+// so the CPU emulation harness in tests/ can run the identical code path without a GPU.
+//
+// Element algebra (DESIGN.md "factored tangent"). With channels c,d in {N,N1,N2,N11,N22,N12}, Phi[gp][c][a] the
+// basis table of the element and S the generalised stresses of maf_math.cuh:
+//   r_el[(a,I)]        = sum_gp w  sum_c     Phi[gp][c][a] S[gp][(I,c)]                       (+ DB term)
+//   K_el[(a,I),(b,J)]  = sum_gp    sum_{c,d} Phi[gp][c][a] A[gp][(I,c)][(J,d)] Phi[gp][d][b]  (+ DB term)
+// where A[gp] = w * (dS/dcps-channel + dt * dS/dx-channel) is the exact Gauss-point tangent; the x-derivative
+// is merged into the column of the dof that moves the mesh (FiniteElement.jl:118-123).
+#pragma once
+#include <stdint.h>
+
+#include "maf_math.cuh"
+
+namespace maf {
+
+enum { F_V = 0, F_M = 1, F_L = 2, F_P = 3, NFIELD = 4 };
+enum { IT_GEO_A = 0, IT_GEO_B = 1, IT_LIN = 2 };
+
+struct Block {      // one (row field, col field) tangent block type
+  int8_t f, g;      // row / col field
+  int8_t c0, nr;    // row channel range [c0, c0+nr)
+  int8_t d0, nc;    // col channel range [d0, d0+nc)
+  int8_t kind;      // dispatch id for the <NR,NC> instantiation
+  int8_t db;        // add the Dohrmann-Bochev matrix (lambda-lambda and pm-pm blocks)
+};
+struct Task {       // 27 outputs of one block: rows (a1 = 0..2, a2), all 9 column nodes b
+  uint8_t blk, i, j, a2;
+};
+struct Item {       // phase-G work item of one Gauss point
+  uint8_t type, gp, gamma, j;
+};
+
+#define MAF_MAX_BLOCKS 12
+#define MAF_MAX_TASKS 160
+#define MAF_MAX_ITEMS 96
+#define MAF_MAX_SLOTS 512
+
+struct Config {
+  int motion, ndf;
+  int mesh_field;                 // field whose dofs move the mesh: F_V (LAG), F_M (EUL/ALE), -1 (STATIC)
+  int fdof[NFIELD][3];            // dof column (0-based) of component i of field f, -1 = absent
+  int ncomp[NFIELD];
+  // Gauss-point tangent storage: one matrix per row field f, rows (i, c in [rc0,rc0+rnc)), row length ald[f];
+  // the columns of field g start at coloff[f][g] (-1: block absent) and hold (j, d in [cd0[f][g], +cnc[f][g])).
+  int rc0[NFIELD], rnc[NFIELD];
+  int cd0[NFIELD][NFIELD], cnc[NFIELD][NFIELD];
+  int aoff[NFIELD], ald[NFIELD], coloff[NFIELD][NFIELD];
+  int asize;                      // doubles per Gauss point
+  int nblocks;
+  Block blocks[MAF_MAX_BLOCKS];
+  int ntasks;
+  Task tasks[MAF_MAX_TASKS];
+  int nitems;
+  Item items[MAF_MAX_ITEMS];
+  // thread -> work maps (host-built so that lanes of a warp share the code path): slot s of round r
+  int nthreads;                   // threads per element
+  int item_rounds, task_rounds;
+  int16_t item_slot[MAF_MAX_SLOTS];   // [round][tid] -> item id or -1
+  int16_t task_slot[MAF_MAX_SLOTS];   // [round][tid] -> task id or -1
+  uint8_t rowmask[8];             // per column dof J: bitmask of row dofs I whose block is in the pattern
+  Material mat;
+  double dbscale;                 // adb / zv
+  // shared-memory layout (offsets in doubles from the element's block)
+  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_A, o_int, smem_doubles;
+};
+
+// interpolated Gauss-point inputs E[gp][.]
+enum { E_A = 0, E_C = 6, E_DV = 15, E_V = 21, E_DM = 24, E_VM = 30, E_LAM = 33, E_PM = 34, E_STRIDE = 36 };
+// primal generalised stresses S[gp][.] : Sv[c][i] at 3c+i, Sm at 18+3c+i, Sl 36, Sp 37
+enum { S_V = 0, S_M = 18, S_L = 36, S_P = 37, S_STRIDE = 38 };
+// integer scratch (int32 view of the o_int region)
+enum { I_NODE = 0, I_EQ = 9, I_MASK = 81, I_PAIR = 90, I_END = 171 };
+
+// read-only device tables shared by all elements
+struct Tables {
+  const int32_t* IX;        // 9 x numel, 0-based node ids
+  const int32_t* ID;        // ndf x numnp, 0-based equation number or -1
+  const uint8_t* nodemask;  // numnp: bit I set if dof I of the node is active
+  const int32_t* uel1;      // num1el, 0-based unique-element id in direction 1
+  const int32_t* uel2;      // num2el
+  const double* line1;      // nuel1 x 3 x 10
+  const double* line2;      // nuel2 x 3 x 10
+  const double* tdb;        // (nuel1*nuel2) x 81 Dohrmann-Bochev matrices G^T H^-1 G (FiniteElement.jl:323)
+  const int64_t* colptr;    // nmdf+1, 0-based
+  const int32_t* elpair;    // numel x 81: index of (A = node a, B = node b) in the node-adjacency list of B
+  const uint8_t* pairoff;   // npairs x 8: rows that precede node A's rows in column (B,J)
+  int64_t numnp, numel;
+  int num1el, nuel1;
+};
+
+#if defined(__CUDA_ARCH__)
+MAF_HD void atomic_add(double* p, double v) { atomicAdd(p, v); }
+#else
+MAF_HD void atomic_add(double* p, double v) { *p += v; }
+#endif
+MAF_HD int popc8(unsigned x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Phase 0: gather the element's nodal data, integer maps and basis table into shared memory.
+// FiniteElement.jl:100-101 (xms_el, cps_el), Mesh.jl:311-319 (table lookup by unique element).
+// ---------------------------------------------------------------------------------------------------------
+MAF_HD void phase_gather(int tid, int nt, const Config& cfg, const Tables& T, int64_t el, const double* xms,
+                         const double* cps, double* sm) {
+  int32_t* si = reinterpret_cast<int32_t*>(sm + cfg.o_int);
+  const int64_t np = T.numnp;
+  for (int k = tid; k < 9 * 14; k += nt) {
+    const int a = k % 9, q = k / 9;
+    const int64_t node = T.IX[9 * el + a];
+    if (q < 3) {
+      sm[cfg.o_x + 9 * q + a] = xms[node + np * q];
+    } else if (q < 11) {
+      // q-3 enumerates (field, comp): v0 v1 v2 m0 m1 m2 l p
+      const int u = q - 3;
+      const int f = u < 3 ? F_V : (u < 6 ? F_M : (u == 6 ? F_L : F_P));
+      const int i = u < 6 ? u % 3 : 0;
+      const int dof = cfg.fdof[f][i];
+      const double val = dof >= 0 ? cps[node + np * dof] : 0.0;  // absent dofs read as zero (GeoDynStress.jl:196-202)
+      const int base = f == F_V ? cfg.o_cv : (f == F_M ? cfg.o_cm : (f == F_L ? cfg.o_cl : cfg.o_cp));
+      sm[base + 9 * i + a] = val;
+    } else if (q == 11) {
+      si[I_NODE + a] = (int32_t)node;
+      si[I_MASK + a] = T.nodemask[node];
+    } else if (q == 12) {
+      for (int d = 0; d < 8; ++d) si[I_EQ + 8 * a + d] = d < cfg.ndf ? T.ID[(int64_t)cfg.ndf * node + d] : -1;
+    } else {
+      for (int b = 0; b < 9; ++b) si[I_PAIR + 9 * a + b] = T.elpair[81 * el + 9 * a + b];
+    }
+  }
+  // basis table of this element: Phi[gp][c][a] = (1-D factor dir 1) * (1-D factor dir 2), one product each
+  const int e1 = (int)(el % T.num1el), e2 = (int)(el / T.num1el);
+  const double* l1 = T.line1 + 30 * T.uel1[e1];
+  const double* l2 = T.line2 + 30 * T.uel2[e2];
+  for (int k = tid; k < 9 * 54; k += nt) {
+    const int a = k % 9, c = (k / 9) % 6, gp = k / 54;
+    const int g1 = gp % 3, g2 = gp / 3, a1 = a % 3, a2 = a / 3;
+    // derivative orders per channel: N(0,0) N1(1,0) N2(0,1) N11(2,0) N22(0,2) N12(1,1)
+    const int o1 = (c == CH_N1 || c == CH_N12) ? 1 : (c == CH_N11 ? 2 : 0);
+    const int o2 = (c == CH_N2 || c == CH_N12) ? 1 : (c == CH_N22 ? 2 : 0);
+    sm[cfg.o_phi + k] = l1[10 * g1 + 1 + 3 * o1 + a1] * l2[10 * g2 + 1 + 3 * o2 + a2];
+  }
+  for (int gp = tid; gp < 9; gp += nt) sm[cfg.o_w + gp] = l1[10 * (gp % 3)] * l2[10 * (gp / 3)];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Phase 1: interpolate the Gauss-point inputs E[gp][.] (GeoDynStress.jl:111-115, 135-143).
+// ---------------------------------------------------------------------------------------------------------
+MAF_HD void phase_interp(int tid, int nt, const Config& cfg, double* sm) {
+  for (int k = tid; k < 9 * 35; k += nt) {
+    const int gp = k / 35, q = k % 35;
+    int src, ch;
+    if (q < 6) { ch = CH_N1 + q / 3; src = cfg.o_x + 9 * (q % 3); }
+    else if (q < 15) { ch = CH_N11 + (q - 6) / 3; src = cfg.o_x + 9 * ((q - 6) % 3); }
+    else if (q < 21) { ch = CH_N1 + (q - 15) / 3; src = cfg.o_cv + 9 * ((q - 15) % 3); }
+    else if (q < 24) { ch = CH_N; src = cfg.o_cv + 9 * (q - 21); }
+    else if (q < 30) { ch = CH_N1 + (q - 24) / 3; src = cfg.o_cm + 9 * ((q - 24) % 3); }
+    else if (q < 33) { ch = CH_N; src = cfg.o_cm + 9 * (q - 30); }
+    else if (q == 33) { ch = CH_N; src = cfg.o_cl; }
+    else { ch = CH_N; src = cfg.o_cp; }
+    const double* ph = sm + cfg.o_phi + 54 * gp + 9 * ch;
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) s += sm[src + a] * ph[a];
+    sm[cfg.o_E + E_STRIDE * gp + q] = s;
+  }
+}
+
+// helper: address of A[gp][(f,i,c)][(g,j,d)]
+MAF_HD int a_index(const Config& cfg, int f, int i, int c, int g, int j, int d) {
+  return cfg.aoff[f] + (i * cfg.rnc[f] + (c - cfg.rc0[f])) * cfg.ald[f] + cfg.coloff[f][g] + j * cfg.cnc[f][g] +
+         (d - cfg.cd0[f][g]);
+}
+
+// store one tangent column (direction = trial (g, j, d)) for every row field that has a (f,g) block containing d
+template <class T>
+MAF_HD void store_column(const Config& cfg, double* Agp, double w, const GpStress<T>& S, int g, int j, int d) {
+#pragma unroll
+  for (int f = 0; f < NFIELD; ++f) {
+    if (cfg.coloff[f][g] < 0) continue;
+    if (d < cfg.cd0[f][g] || d >= cfg.cd0[f][g] + cfg.cnc[f][g]) continue;
+    if (f == F_V || f == F_M) {
+      for (int i = 0; i < 3; ++i)
+        for (int c = cfg.rc0[f]; c < cfg.rc0[f] + cfg.rnc[f]; ++c)
+          Agp[a_index(cfg, f, i, c, g, j, d)] = w * der(f == F_V ? S.Sv[c][i] : S.Sm[c][i]);
+    } else {
+      Agp[a_index(cfg, f, 0, CH_N, g, j, d)] = w * der(f == F_L ? S.Sl : S.Sp);
+    }
+  }
+}
+
+MAF_HD void load_E(const double* E, double a[2][3], double c[3][3], double dv[2][3], double v[3], double dm[2][3],
+                   double vm[3], double& lam, double& pm) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    a[0][i] = E[E_A + i]; a[1][i] = E[E_A + 3 + i];
+    c[0][i] = E[E_C + i]; c[1][i] = E[E_C + 3 + i]; c[2][i] = E[E_C + 6 + i];
+    dv[0][i] = E[E_DV + i]; dv[1][i] = E[E_DV + 3 + i];
+    v[i] = E[E_V + i];
+    dm[0][i] = E[E_DM + i]; dm[1][i] = E[E_DM + 3 + i];
+    vm[i] = E[E_VM + i];
+  }
+  lam = E[E_LAM];
+  pm = E[E_PM];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Phase 2: Gauss-point tangent A[gp] (exact derivative) and primal S[gp].
+//  IT_GEO_A (gamma, j): direction d x_{,gamma}_j = dt, d (mesh velocity)_{,gamma}_j = 1  -> column (mesh, j, N_gamma)
+//  IT_GEO_B           : directions d x_{,k}_j = dt for the three second derivatives      -> columns (mesh, j, N_k)
+//  IT_LIN             : primal S, and the closed-form columns of the dofs that do not move the mesh
+// ---------------------------------------------------------------------------------------------------------
+template <int MOTION>
+MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, double* sm) {
+  const int gp = it.gp;
+  const double* E = sm + cfg.o_E + E_STRIDE * gp;
+  double* Agp = sm + cfg.o_A + (size_t)cfg.asize * gp;
+  const double w = sm[cfg.o_w + gp];
+  double a[2][3], c[3][3], dv[2][3], v[3], dm[2][3], vm[3], lam, pm;
+  load_E(E, a, c, dv, v, dm, vm, lam, pm);
+  const int mf = cfg.mesh_field;
+
+  if (it.type == IT_GEO_A) {
+    Dual ad[2][3];
+#pragma unroll
+    for (int al = 0; al < 2; ++al)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ad[al][i] = Dual(a[al][i], (al == it.gamma && i == it.j) ? dt : 0.0);
+    GpStress<Dual> S;
+    if (MOTION == M_LAG) {  // mesh velocity = v
+      Dual dvd[2][3];
+#pragma unroll
+      for (int al = 0; al < 2; ++al)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) dvd[al][i] = Dual(dv[al][i], (al == it.gamma && i == it.j) ? 1.0 : 0.0);
+      Dual vd[3] = {Dual(v[0]), Dual(v[1]), Dual(v[2])};
+      gp_eval<MOTION, Dual, double, Dual, double, double>(ad, c, dvd, vd, dm, vm, lam, pm, cfg.mat, S);
+    } else {               // mesh velocity = vm
+      Dual dmd[2][3];
+#pragma unroll
+      for (int al = 0; al < 2; ++al)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) dmd[al][i] = Dual(dm[al][i], (al == it.gamma && i == it.j) ? 1.0 : 0.0);
+      Dual vmd[3] = {Dual(vm[0]), Dual(vm[1]), Dual(vm[2])};
+      gp_eval<MOTION, Dual, double, double, Dual, double>(ad, c, dv, v, dmd, vmd, lam, pm, cfg.mat, S);
+    }
+    store_column(cfg, Agp, w, S, mf, it.j, CH_N1 + it.gamma);
+  } else if (it.type == IT_GEO_B) {
+    for (int k = 0; k < 3; ++k)
+      for (int j = 0; j < 3; ++j) {
+        Dual cd[3][3];
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) cd[kk][i] = Dual(c[kk][i], (kk == k && i == j) ? dt : 0.0);
+        GpStress<Dual> S;
+        gp_eval<MOTION, double, Dual, double, double, double>(a, cd, dv, v, dm, vm, lam, pm, cfg.mat, S);
+        store_column(cfg, Agp, w, S, mf, j, CH_N11 + k);
+      }
+  } else {
+    // primal stresses -> S[gp]
+    GpStress<double> S;
+    gp_eval<MOTION, double, double, double, double, double>(a, c, dv, v, dm, vm, lam, pm, cfg.mat, S);
+    double* Sg = sm + cfg.o_S + S_STRIDE * gp;
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { Sg[S_V + 3 * cc + i] = S.Sv[cc][i]; Sg[S_M + 3 * cc + i] = S.Sm[cc][i]; }
+    Sg[S_L] = S.Sl;
+    Sg[S_P] = S.Sp;
+    // closed-form columns of the dofs that do not move the mesh (the residual is affine in cps at fixed x)
+    for (int j = 0; j < 3; ++j) {
+      if (mf != F_V) {  // velocity gradient channels (v, j, N_mu), mu = 1,2 : viscous tangent + incompressibility
+        for (int mu = 0; mu < 2; ++mu) {
+          Dual dvd[2][3];
+#pragma unroll
+          for (int al = 0; al < 2; ++al)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) dvd[al][i] = Dual(dv[al][i], (al == mu && i == j) ? 1.0 : 0.0);
+          Dual vd[3] = {Dual(v[0]), Dual(v[1]), Dual(v[2])};
+          GpStress<Dual> Sd;
+          gp_eval<MOTION, double, double, Dual, double, double>(a, c, dvd, vd, dm, vm, lam, pm, cfg.mat, Sd);
+          store_column(cfg, Agp, w, Sd, F_V, j, CH_N1 + mu);
+        }
+        if (MOTION == M_EUL || MOTION == M_ALEV || MOTION == M_ALEVB) {  // value channel (v, j, N)
+          Dual dvd[2][3];
+#pragma unroll
+          for (int al = 0; al < 2; ++al)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) dvd[al][i] = Dual(dv[al][i]);
+          Dual vd[3] = {Dual(v[0], j == 0 ? 1.0 : 0.0), Dual(v[1], j == 1 ? 1.0 : 0.0), Dual(v[2], j == 2 ? 1.0 : 0.0)};
+          GpStress<Dual> Sd;
+          gp_eval<MOTION, double, double, Dual, double, double>(a, c, dvd, vd, dm, vm, lam, pm, cfg.mat, Sd);
+          store_column(cfg, Agp, w, Sd, F_V, j, CH_N);
+        }
+      }
+      if (MOTION == M_EUL || MOTION == M_ALEV || MOTION == M_ALEVB) {  // (vm, j, N)
+        Dual dmd[2][3];
+#pragma unroll
+        for (int al = 0; al < 2; ++al)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) dmd[al][i] = Dual(dm[al][i]);
+        Dual vmd[3] = {Dual(vm[0], j == 0 ? 1.0 : 0.0), Dual(vm[1], j == 1 ? 1.0 : 0.0), Dual(vm[2], j == 2 ? 1.0 : 0.0)};
+        GpStress<Dual> Sd;
+        gp_eval<MOTION, double, double, double, Dual, double>(a, c, dv, v, dmd, vmd, lam, pm, cfg.mat, Sd);
+        store_column(cfg, Agp, w, Sd, F_M, j, CH_N);
+      }
+    }
+    {  // (lambda, N)
+      GpStress<Dual> Sd;
+      gp_eval<MOTION, double, double, double, double, Dual>(a, c, dv, v, dm, vm, Dual(lam, 1.0), Dual(pm), cfg.mat, Sd);
+      store_column(cfg, Agp, w, Sd, F_L, 0, CH_N);
+    }
+    if (MOTION == M_ALEV || MOTION == M_ALEVB) {  // (pm, N)
+      GpStress<Dual> Sd;
+      gp_eval<MOTION, double, double, double, double, Dual>(a, c, dv, v, dm, vm, Dual(lam), Dual(pm, 1.0), cfg.mat, Sd);
+      store_column(cfg, Agp, w, Sd, F_P, 0, CH_N);
+    }
+  }
+}
+
+template <int MOTION>
+MAF_HD void phase_gauss(int tid, const Config& cfg, double dt, double* sm) {
+  for (int r = 0; r < cfg.item_rounds; ++r) {
+    const int id = cfg.item_slot[r * cfg.nthreads + tid];
+    if (id >= 0) phase_gauss_item<MOTION>(cfg, cfg.items[id], dt, sm);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Phase 3a: element residual r_el and its scatter (FiniteElement.jl:103, 129-131).
+// ---------------------------------------------------------------------------------------------------------
+MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const Tables& T, int64_t el, double* sm, double* r_gl,
+                           double* r_stage /* deterministic path: 72 staged rows of this element, or NULL */) {
+  const int32_t* si = reinterpret_cast<const int32_t*>(sm + cfg.o_int);
+  const int e1 = (int)(el % T.num1el), e2 = (int)(el / T.num1el);
+  const double* tdb = T.tdb + 81 * ((int64_t)T.uel1[e1] + (int64_t)T.nuel1 * T.uel2[e2]);
+  for (int k = tid; k < 72; k += nt) {
+    const int a = k % 9, u = k / 9;
+    const int f = u < 3 ? F_V : (u < 6 ? F_M : (u == 6 ? F_L : F_P));
+    const int i = u < 6 ? u % 3 : 0;
+    const int dof = cfg.fdof[f][i];
+    const int eq = dof >= 0 ? si[I_EQ + 8 * a + dof] : -1;
+    if (eq < 0) {  // rows of inactive dofs are discarded (FiniteElement.jl:107,129)
+      if (r_stage) r_stage[k] = 0.0;
+      continue;
+    }
+    double s = 0.0;
+    for (int gp = 0; gp < 9; ++gp) {
+      const double* Sg = sm + cfg.o_S + S_STRIDE * gp;
+      const double* ph = sm + cfg.o_phi + 54 * gp;
+      double t;
+      if (f == F_V || f == F_M) {
+        const int sb = f == F_V ? S_V : S_M;
+        t = 0.0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) t += Sg[sb + 3 * c + i] * ph[9 * c + a];
+      } else {
+        t = Sg[f == F_L ? S_L : S_P] * ph[a];
+      }
+      s += sm[cfg.o_w + gp] * t;
+    }
+    if (f == F_L || (f == F_P)) {  // Dohrmann-Bochev projection of the nodal lambda / pm (FiniteElement.jl:323-327)
+      const double* nod = sm + (f == F_L ? cfg.o_cl : cfg.o_cp);
+      double t = 0.0;
+#pragma unroll
+      for (int b = 0; b < 9; ++b) t += tdb[9 * a + b] * nod[b];
+      s += cfg.dbscale * t;
+    }
+    if (r_stage) r_stage[k] = s; else atomic_add(&r_gl[eq], s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Phase 3b: one tangent task = 27 entries of K_el (rows a = a1 + 3 a2, a1 = 0..2; all column nodes b)
+// of one (row dof I, col dof J) block, accumulated over the 9 Gauss points in registers.
+// ---------------------------------------------------------------------------------------------------------
+template <int NR, int NC>
+MAF_HD void block_accumulate(const double* __restrict__ A0, int asize, int ald, const double* __restrict__ Phi,
+                             int c0, int d0, int a2, double acc[3][9]) {
+#pragma unroll
+  for (int a1 = 0; a1 < 3; ++a1)
+#pragma unroll
+    for (int b = 0; b < 9; ++b) acc[a1][b] = 0.0;
+  for (int gp = 0; gp < 9; ++gp) {
+    const double* Ag = A0 + (size_t)asize * gp;
+    const double* Pg = Phi + 54 * gp;
+    double u[3][NC];
+#pragma unroll
+    for (int a1 = 0; a1 < 3; ++a1)
+#pragma unroll
+      for (int d = 0; d < NC; ++d) u[a1][d] = 0.0;
+#pragma unroll
+    for (int c = 0; c < NR; ++c) {
+      const double p0 = Pg[9 * (c0 + c) + 3 * a2], p1 = Pg[9 * (c0 + c) + 3 * a2 + 1], p2 = Pg[9 * (c0 + c) + 3 * a2 + 2];
+#pragma unroll
+      for (int d = 0; d < NC; ++d) {
+        const double av = Ag[c * ald + d];
+        u[0][d] += p0 * av;
+        u[1][d] += p1 * av;
+        u[2][d] += p2 * av;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < NC; ++d)
+#pragma unroll
+      for (int b = 0; b < 9; ++b) {
+        const double pb = Pg[9 * (d0 + d) + b];
+        acc[0][b] += u[0][d] * pb;
+        acc[1][b] += u[1][d] * pb;
+        acc[2][b] += u[2][d] * pb;
+      }
+  }
+}
+
+// destination of the 27 outputs of a task
+struct KSink {
+  double* nzval;            // atomics path: global CSC values
+  double* kel;              // deterministic path: this element's staging rows [a*9+b][nij], or NULL
+  const int16_t* task_ij;   // deterministic path: per task, column of its (row dof, col dof) class in a staging row
+  int nij;
+};
+
+MAF_HD void phase_tangent_task(const Config& cfg, const Tables& T, int64_t el, int task_id, const double* sm,
+                               const KSink& sink) {
+  const Task tk = cfg.tasks[task_id];
+  const Block bk = cfg.blocks[tk.blk];
+  const int f = bk.f, g = bk.g, i = tk.i, j = tk.j, a2 = tk.a2;
+  const double* A0 = sm + cfg.o_A + a_index(cfg, f, i, bk.c0, g, j, bk.d0);
+  const double* Phi = sm + cfg.o_phi;
+  const int ald = cfg.ald[f];
+  double acc[3][9];
+  switch (bk.kind) {
+    case 0: block_accumulate<1, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
+    case 1: block_accumulate<1, 2>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
+    case 2: block_accumulate<1, 3>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
+    case 3: block_accumulate<2, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
+    case 4: block_accumulate<2, 2>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
+    case 5: block_accumulate<3, 5>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
+    case 6: block_accumulate<5, 5>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
+    default: block_accumulate<6, 5>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
+  }
+  const int32_t* si = reinterpret_cast<const int32_t*>(sm + cfg.o_int);
+  if (bk.db) {  // Dohrmann-Bochev stabilisation matrix (state independent), FiniteElement.jl:323-327
+    const int e1 = (int)(el % T.num1el), e2 = (int)(el / T.num1el);
+    const double* tdb = T.tdb + 81 * ((int64_t)T.uel1[e1] + (int64_t)T.nuel1 * T.uel2[e2]);
+#pragma unroll
+    for (int a1 = 0; a1 < 3; ++a1)
+#pragma unroll
+      for (int b = 0; b < 9; ++b) acc[a1][b] += cfg.dbscale * tdb[9 * (a1 + 3 * a2) + b];
+  }
+  if (sink.kel) {  // deterministic path: stage, a gather kernel sums in ascending element order
+    double* dst = sink.kel + sink.task_ij[task_id];
+#pragma unroll
+    for (int a1 = 0; a1 < 3; ++a1)
+#pragma unroll
+      for (int b = 0; b < 9; ++b) dst[(size_t)(9 * (a1 + 3 * a2) + b) * sink.nij] = acc[a1][b];
+    return;
+  }
+  // atomics path: K_gl[LM[i], LM[j]] += K_el[i, j] for active rows and columns (FiniteElement.jl:129-136)
+  const int I = cfg.fdof[f][i], J = cfg.fdof[g][j];
+  const unsigned rmask = cfg.rowmask[J];
+#pragma unroll
+  for (int b = 0; b < 9; ++b) {
+    const int eqc = si[I_EQ + 8 * b + J];
+    if (eqc < 0) continue;  // columns exist only for active dofs (FiniteElement.jl:111)
+    const int64_t cp = T.colptr[eqc];
+#pragma unroll
+    for (int a1 = 0; a1 < 3; ++a1) {
+      const int a = a1 + 3 * a2;
+      const unsigned m = (unsigned)si[I_MASK + a];
+      if (!((m >> I) & 1u)) continue;
+      const int64_t slot = cp + T.pairoff[(int64_t)si[I_PAIR + 9 * a + b] * 8 + J] + popc8(m & rmask & ((1u << I) - 1u));
+      atomic_add(&sink.nzval[slot], acc[a1][b]);
+    }
+  }
+}
+
+MAF_HD void phase_tangent(int tid, const Config& cfg, const Tables& T, int64_t el, const double* sm, const KSink& sink) {
+  for (int r = 0; r < cfg.task_rounds; ++r) {
+    const int id = cfg.task_slot[r * cfg.nthreads + tid];
+    if (id >= 0) phase_tangent_task(cfg, T, el, id, sm, sink);
+  }
+}
+
+}  // namespace maf

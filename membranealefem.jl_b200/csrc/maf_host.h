@@ -1,0 +1,167 @@
+// maf_host.h -- validation of the C-ABI inputs and construction of everything the kernels read
+// (0-based int32 index tables, kernel configuration, symbolic pattern, Dohrmann-Bochev matrices, boundary lists).
+// Pure C++; used by the library (which uploads the result) and by the CPU emulation harness in tests/.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/maf.h"
+#include "maf_boundary.cuh"
+#include "maf_config.h"
+#include "maf_gather.cuh"
+#include "maf_symbolic.h"
+
+namespace maf {
+
+struct HostModel {
+  Config cfg;
+  Symbolic sym;
+  int64_t numel = 0, numnp = 0, nmdf = 0;
+  int ndf = 0, num1el = 0, num2el = 0, nuel1 = 0, nuel2 = 0, motion = 0, scenario = 0, pattern_mode = 0;
+  std::vector<int32_t> IX0, ID0, uel1, uel2;
+  std::vector<double> line1, line2, edge1, edge2, tdb;
+  std::vector<int32_t> b_elems, b_offs, b_bdry, b_type;
+  std::vector<double> b_val;
+  int n_neu = 0;
+};
+
+#define MAF_REQUIRE(cond, msg)                         \
+  do {                                                 \
+    if (!(cond)) throw std::runtime_error(std::string(msg)); \
+  } while (0)
+
+inline void build_host_model(HostModel& M, const maf_mesh_desc* d, const maf_params* p, int nthreads) {
+  MAF_REQUIRE(d && p, "null mesh descriptor or params");
+  MAF_REQUIRE(d->numel > 0 && d->numnp > 0, "empty mesh");
+  MAF_REQUIRE(d->ndf >= 3 && d->ndf <= 8, "ndf must be in 3..8");
+  MAF_REQUIRE(d->num1el > 0 && d->num2el > 0 && d->num1el * d->num2el == d->numel, "numel != num1el*num2el");
+  MAF_REQUIRE(d->numnp < ((int64_t)1 << 31) && d->numel < ((int64_t)1 << 31) / 81, "mesh too large for int32 tables");
+  MAF_REQUIRE(d->IX && d->ID && d->uel_ids1 && d->uel_ids2 && d->line1 && d->line2 && d->edge1 && d->edge2,
+              "null table pointer");
+  MAF_REQUIRE(p->motion >= 1 && p->motion <= 5, "unknown motion code");
+  MAF_REQUIRE(p->zv != 0.0, "membrane viscosity must be non-zero");
+  M.numel = d->numel; M.numnp = d->numnp; M.nmdf = d->nmdf; M.ndf = (int)d->ndf;
+  M.num1el = (int)d->num1el; M.num2el = (int)d->num2el; M.nuel1 = (int)d->nuel1; M.nuel2 = (int)d->nuel2;
+  M.motion = p->motion; M.scenario = p->scenario; M.pattern_mode = p->pattern_mode;
+  for (int u = 0; u < 8; ++u) MAF_REQUIRE(d->dofs[u] >= 0 && d->dofs[u] <= d->ndf, "dofs entry outside 0..ndf");
+
+  M.IX0.resize((size_t)9 * M.numel);
+  for (size_t k = 0; k < M.IX0.size(); ++k) {
+    MAF_REQUIRE(d->IX[k] >= 1 && d->IX[k] <= M.numnp, "IX entry outside 1..numnp");
+    M.IX0[k] = (int32_t)(d->IX[k] - 1);
+  }
+  M.ID0.resize((size_t)M.ndf * M.numnp);
+  int64_t maxeq = 0;
+  for (size_t k = 0; k < M.ID0.size(); ++k) {
+    MAF_REQUIRE(d->ID[k] >= 0 && d->ID[k] <= M.nmdf, "ID entry outside 0..nmdf");
+    M.ID0[k] = (int32_t)(d->ID[k] - 1);
+    maxeq = std::max(maxeq, d->ID[k]);
+  }
+  MAF_REQUIRE(maxeq == M.nmdf, "nmdf != maximum(ID)");
+  // node-major numbering (Mesh.jl:276-284) is what makes the CSC rows come out sorted
+  {
+    int64_t next = 1;
+    for (size_t k = 0; k < M.ID0.size(); ++k)
+      if (d->ID[k] != 0) { MAF_REQUIRE(d->ID[k] == next, "ID is not numbered node-major (Mesh.jl:276-284)"); ++next; }
+  }
+  if (d->LM) {
+    const int nd = 9 * M.ndf;
+    for (int64_t e = 0; e < M.numel; ++e)
+      for (int a = 0; a < 9; ++a)
+        for (int q = 0; q < M.ndf; ++q)
+          MAF_REQUIRE(d->LM[(size_t)q + (size_t)M.ndf * a + (size_t)nd * e] ==
+                          d->ID[(size_t)q + (size_t)M.ndf * (d->IX[(size_t)a + 9 * (size_t)e] - 1)],
+                      "LM != ID[:, IX] (Mesh.jl:299)");
+  }
+  M.uel1.resize(M.num1el);
+  M.uel2.resize(M.num2el);
+  for (int k = 0; k < M.num1el; ++k) {
+    MAF_REQUIRE(d->uel_ids1[k] >= 1 && d->uel_ids1[k] <= M.nuel1, "uel_ids1 entry outside 1..nuel1");
+    M.uel1[k] = (int32_t)(d->uel_ids1[k] - 1);
+  }
+  for (int k = 0; k < M.num2el; ++k) {
+    MAF_REQUIRE(d->uel_ids2[k] >= 1 && d->uel_ids2[k] <= M.nuel2, "uel_ids2 entry outside 1..nuel2");
+    M.uel2[k] = (int32_t)(d->uel_ids2[k] - 1);
+  }
+  M.line1.assign(d->line1, d->line1 + (size_t)30 * M.nuel1);
+  M.line2.assign(d->line2, d->line2 + (size_t)30 * M.nuel2);
+  M.edge1.assign(d->edge1, d->edge1 + 20);
+  M.edge2.assign(d->edge2, d->edge2 + 20);
+  for (double v : M.line1) MAF_REQUIRE(std::isfinite(v), "non-finite basis table entry");
+  for (double v : M.line2) MAF_REQUIRE(std::isfinite(v), "non-finite basis table entry");
+
+  build_config(M.cfg, p->motion, M.ndf, d->dofs, p->kb, p->kg, p->zv, p->pn, p->adb, p->am,
+               p->pattern_mode == MAF_PATTERN_SYM, nthreads);
+  build_symbolic(M.sym, M.numel, M.numnp, M.ndf, M.nmdf, M.IX0.data(), M.ID0.data(), M.cfg.rowmask);
+  build_tdb(M.nuel1, M.nuel2, M.line1.data(), M.line2.data(), d->xi, M.tdb);
+
+  // Neumann conditions in the reference's order (FiniteElement.jl:151-154)
+  M.n_neu = d->n_neu;
+  M.b_offs.assign(1, 0);
+  for (int k = 0; k < d->n_neu; ++k) {
+    const int bd = d->neu_bdry[k], ty = d->neu_type[k];
+    MAF_REQUIRE(bd >= 1 && bd <= 4, "unknown Boundary code");
+    MAF_REQUIRE(ty >= 1 && ty <= 3, "unknown Neumann code");
+    // FiniteElement.jl:377-383: MOMENT is implemented for F_BEND only, anything else asserts
+    MAF_REQUIRE(ty != MAF_MOMENT || p->scenario == MAF_F_BEND, "Neumann boundary condition not implemented");
+    MAF_REQUIRE(d->bdry_elems[bd - 1] || d->bdry_count[bd - 1] == 0, "null boundary element list");
+    for (int64_t q = 0; q < d->bdry_count[bd - 1]; ++q) {
+      const int64_t e = d->bdry_elems[bd - 1][q];
+      MAF_REQUIRE(e >= 1 && e <= M.numel, "boundary element id outside 1..numel");
+      M.b_elems.push_back((int32_t)(e - 1));
+    }
+    M.b_offs.push_back((int32_t)M.b_elems.size());
+    M.b_bdry.push_back(bd);
+    M.b_type.push_back(ty);
+    M.b_val.push_back(d->neu_val[k]);
+  }
+}
+
+inline Tables host_tables(const HostModel& M) {
+  Tables T;
+  T.IX = M.IX0.data(); T.ID = M.ID0.data(); T.nodemask = M.sym.nodemask.data();
+  T.uel1 = M.uel1.data(); T.uel2 = M.uel2.data(); T.line1 = M.line1.data(); T.line2 = M.line2.data();
+  T.tdb = M.tdb.data(); T.colptr = M.sym.colptr.data(); T.elpair = M.sym.elpair.data();
+  T.pairoff = M.sym.pairoff.data(); T.numnp = M.numnp; T.numel = M.numel; T.num1el = M.num1el; T.nuel1 = M.nuel1;
+  return T;
+}
+inline BoundaryTables host_boundary_tables(const HostModel& M) {
+  BoundaryTables B;
+  B.edge1 = M.edge1.data(); B.edge2 = M.edge2.data(); B.elems = M.b_elems.data(); B.offs = M.b_offs.data();
+  B.bdry = M.b_bdry.data(); B.ntype = M.b_type.data(); B.nval = M.b_val.data(); B.n_neu = M.n_neu;
+  return B;
+}
+
+// value multiplying the traction of a condition: nval, or Mval = nval*min(time/bend_tm, 1) (FiniteElement.jl:379)
+inline double neumann_value(int ntype, double nval, double time, double bend_tm) {
+  return ntype == MAF_MOMENT ? nval * std::min(time / bend_tm, 1.0) : nval;
+}
+
+// host tables of the deterministic path
+struct GatherHost {
+  std::vector<int32_t> pair_node;
+  std::vector<int16_t> ij_of, task_ij;
+  int nij = 0;
+};
+inline void build_gather_host(const HostModel& M, GatherHost& GH) {
+  const Symbolic& S = M.sym;
+  GH.pair_node.resize(S.npairs);
+  for (int64_t B = 0; B < M.numnp; ++B)
+    for (int64_t p = S.nbr_ptr[B]; p < S.nbr_ptr[B + 1]; ++p) GH.pair_node[p] = (int32_t)B;
+  // (I,J) classes = distinct (row dof, col dof) pairs that own tangent tasks
+  GH.ij_of.assign(64, -1);
+  GH.task_ij.assign(M.cfg.ntasks, -1);
+  GH.nij = 0;
+  for (int t = 0; t < M.cfg.ntasks; ++t) {
+    const Task& tk = M.cfg.tasks[t];
+    const Block& bk = M.cfg.blocks[tk.blk];
+    const int I = M.cfg.fdof[bk.f][tk.i], J = M.cfg.fdof[bk.g][tk.j];
+    if (GH.ij_of[8 * I + J] < 0) GH.ij_of[8 * I + J] = (int16_t)GH.nij++;
+    GH.task_ij[t] = GH.ij_of[8 * I + J];
+  }
+}
+
+}  // namespace maf

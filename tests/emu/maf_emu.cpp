@@ -1,0 +1,118 @@
+// tests/emu/maf_emu.cpp -- TEST INFRASTRUCTURE. Runs the library's element / boundary phase functions
+// (membranealefem.jl_b200/csrc/maf_element.cuh, maf_boundary.cuh -- the exact code the CUDA kernels execute)
+// on the CPU by looping the "threads" of a CTA between barriers. Lets the no-GPU container validate the kernel
+// logic, the symbolic phase and the scatter maps against the oracle. Never loaded by the product.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../membranealefem.jl_b200/csrc/maf_host.h"
+
+using namespace maf;
+
+static std::string g_err;
+
+template <int MOTION>
+static void run_area(const HostModel& M, const Tables& T, const double* xms, const double* cps, double dt, double* r,
+                     double* nzval, double* kel, double* rel, const GatherHost* GH, int64_t e0, int64_t e1) {
+  const Config& cfg = M.cfg;
+  const int nt = cfg.nthreads;
+  std::vector<double> sm(cfg.smem_doubles);
+  for (int64_t el = e0; el < e1; ++el) {
+    std::fill(sm.begin(), sm.end(), std::nan(""));  // any read of an unwritten slot poisons the result
+    for (int t = 0; t < nt; ++t) phase_gather(t, nt, cfg, T, el, xms, cps, sm.data());
+    for (int t = 0; t < nt; ++t) phase_interp(t, nt, cfg, sm.data());
+    for (int t = 0; t < nt; ++t) phase_gauss<MOTION>(t, cfg, dt, sm.data());
+    KSink sink{nzval, nullptr, nullptr, 0};
+    if (kel) sink = KSink{nullptr, kel + (size_t)81 * GH->nij * (el - e0), GH->task_ij.data(), GH->nij};
+    for (int t = 0; t < nt; ++t) phase_residual(t, nt, cfg, T, el, sm.data(), r, rel ? rel + 72 * (el - e0) : nullptr);
+    for (int t = 0; t < nt; ++t) phase_tangent(t, cfg, T, el, sm.data(), sink);
+  }
+}
+
+extern "C" {
+
+const char* emu_last_error() { return g_err.c_str(); }
+
+struct emu_model {
+  HostModel M;
+};
+
+void* emu_create(const maf_mesh_desc* d, const maf_params* p, int nthreads) {
+  try {
+    emu_model* m = new emu_model();
+    build_host_model(m->M, d, p, nthreads);
+    return m;
+  } catch (std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+void emu_destroy(void* h) { delete (emu_model*)h; }
+int64_t emu_nnz(void* h) { return ((emu_model*)h)->M.sym.nnz; }
+void emu_pattern(void* h, int64_t* colptr1, int64_t* rowval1) {
+  HostModel& M = ((emu_model*)h)->M;
+  for (int64_t c = 0; c <= M.nmdf; ++c) colptr1[c] = M.sym.colptr[c] + 1;
+  build_rowval(M.sym, M.ID0.data(), M.cfg.rowmask, rowval1);
+}
+// info: [asize, smem_doubles, ntasks, nitems, item_rounds, task_rounds, nblocks]
+void emu_info(void* h, int64_t* o) {
+  const Config& c = ((emu_model*)h)->M.cfg;
+  o[0] = c.asize; o[1] = c.smem_doubles; o[2] = c.ntasks; o[3] = c.nitems; o[4] = c.item_rounds;
+  o[5] = c.task_rounds; o[6] = c.nblocks;
+}
+
+int emu_assemble(void* h, const double* xms, const double* cps, double time, double dt, double bend_tm, int mode,
+                 int64_t el_first, int64_t el_last, double* r, double* nzval) {
+  try {
+    HostModel& M = ((emu_model*)h)->M;
+    Tables T = host_tables(M);
+    BoundaryTables BT = host_boundary_tables(M);
+    std::memset(r, 0, sizeof(double) * (size_t)M.nmdf);
+    std::memset(nzval, 0, sizeof(double) * (size_t)M.sym.nnz);
+    const int64_t e0 = el_first - 1, e1 = el_last;
+    GatherHost GH;
+    std::vector<double> kel, rel;
+    if (mode == 1) {
+      build_gather_host(M, GH);
+      kel.assign((size_t)81 * GH.nij * (e1 - e0), std::nan(""));
+      rel.assign((size_t)72 * (e1 - e0), std::nan(""));
+      std::fill(r, r + M.nmdf, std::nan(""));
+      std::fill(nzval, nzval + M.sym.nnz, std::nan(""));
+    }
+    double* kp = mode == 1 ? kel.data() : nullptr;
+    double* rp = mode == 1 ? rel.data() : nullptr;
+    switch (M.motion) {
+      case M_STATIC: run_area<M_STATIC>(M, T, xms, cps, dt, r, nzval, kp, rp, &GH, e0, e1); break;
+      case M_EUL: run_area<M_EUL>(M, T, xms, cps, dt, r, nzval, kp, rp, &GH, e0, e1); break;
+      case M_LAG: run_area<M_LAG>(M, T, xms, cps, dt, r, nzval, kp, rp, &GH, e0, e1); break;
+      case M_ALEV: run_area<M_ALEV>(M, T, xms, cps, dt, r, nzval, kp, rp, &GH, e0, e1); break;
+      default: run_area<M_ALEVB>(M, T, xms, cps, dt, r, nzval, kp, rp, &GH, e0, e1); break;
+    }
+    if (mode == 1) {
+      GatherTables G;
+      G.nbr_ptr = M.sym.nbr_ptr.data(); G.nbr = M.sym.nbr.data(); G.pair_node = GH.pair_node.data();
+      G.n2e_ptr = M.sym.n2e_ptr.data(); G.n2e = M.sym.n2e.data(); G.n2e_loc = M.sym.n2e_loc.data();
+      G.ij_of = GH.ij_of.data(); G.npairs = M.sym.npairs;
+      for (int64_t p = 0; p < G.npairs; ++p) gather_K_pair(p, M.cfg, T, G, kel.data(), GH.nij, e0, e1, nzval);
+      for (int64_t k = 0; k < M.numnp * M.ndf; ++k) gather_r_row(k, M.cfg, T, G, rel.data(), e0, e1, r);
+    }
+    std::vector<double> sm(B_DOUBLES);
+    for (int bc = 0; bc < BT.n_neu; ++bc) {
+      const double fval = neumann_value(BT.ntype[bc], BT.nval[bc], time, bend_tm);
+      for (int q = BT.offs[bc]; q < BT.offs[bc + 1]; ++q) {
+        const int64_t el = BT.elems[q];
+        if (el < e0 || el >= e1) continue;
+        std::fill(sm.begin(), sm.end(), std::nan(""));
+        for (int l = 0; l < 32; ++l) boundary_gather(l, 32, M.cfg, T, BT, bc, el, xms, sm.data());
+        for (int l = 0; l < 32; ++l) boundary_gauss(l, 32, M.cfg, BT, bc, fval, dt, sm.data());
+        for (int l = 0; l < 32; ++l) boundary_scatter(l, 32, M.cfg, T, sm.data(), r, nzval, mode == 1);
+      }
+    }
+    return 0;
+  } catch (std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+}
