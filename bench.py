@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- residual + tangent assembly (calc_r_K) throughput on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path (one calc_r_K: area elements + Neumann boundary elements + scatter) over the
+synthetic flat F_PULL patch of BASELINE.json configs[4] (1001 x 1001 = 1 002 001 elements, ALEVB, perturbed state of
+SURVEY.md 8(d)5). `value` = elements/s with the inputs resident in HBM; `e2e` = the same call through the C ABI's
+host-buffer entry point (maf_assemble: H2D of xms/cps, D2H of r and nzval inside the timed region).
+N > 1 (torchrun): the patch is cut into N strips of element rows (strong scaling); after the kernels each rank
+exchanges only the interface rows/entries with its neighbours over NCCL and the residual norm is all-reduced.
+--impl reference times the CPU restatement of the reference algorithm (the reference itself is Julia, which this
+image does not have) on a bounded sample of the same workload with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FP64 residual+tangent assembly throughput (calc_r_K)"
+UNIT = "Melem/s"
+# algorithmic work per element, SURVEY.md 8(d): bytes B_el = 8*25*ndf^2 + 8*ndf + 8*(3+ndf) + 36, FLOPs F_el
+B_EL = {"LAG": 3324, "EUL": 9972, "ALEV": 12988, "ALEVB": 12988}
+F_EL = {"LAG": 0.20e6, "EUL": 0.24e6, "ALEV": 0.41e6, "ALEVB": 0.41e6}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--motion", default="ALEVB", choices=["LAG", "EUL", "ALEV", "ALEVB"])
+    ap.add_argument("--n", type=int, default=1001, help="elements per direction of the synthetic patch")
+    ap.add_argument("--scatter", default="atomic", choices=["atomic", "deterministic"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def lm_pattern(LM, nmdf):
+    """0-based CSC pattern = union over elements of (active LM rows x active LM cols)."""
+    keys = []
+    for e in range(LM.shape[1]):
+        act = LM[:, e][LM[:, e] != 0].astype(np.int64) - 1
+        keys.append((act[None, :] * nmdf + act[:, None]).ravel())       # col * nmdf + row
+    keys = np.unique(np.concatenate(keys))
+    cols, rows = keys // nmdf, keys % nmdf
+    colptr = np.zeros(nmdf + 1, dtype=np.int64)
+    np.add.at(colptr, cols + 1, 1)
+    return np.cumsum(colptr), rows
+
+
+def cpu_reference_rate(motion, steps, warmup, target_s=1.5):
+    """Times the oracle's calc_r_K (complex-step tangent, the reference's chunked threading scheme, private
+    accumulators, sum, serial Neumann loop -- FiniteElement.jl:75-200) on a bounded sample of the workload."""
+    import mafb200 as maf
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    mcode = getattr(orc, motion)
+
+    def setup(n):
+        om = orc.Mesh(motion=mcode, scenario=orc.F_PULL, num1el=n, num2el=n, pull_speed=0.5)
+        p = maf.Params(motion=getattr(maf, motion), scenario=maf.F_PULL, num1el=n, num2el=n, output=False)
+        hm = maf.Mesh(p, pull_speed=0.5)
+        xms, cps = maf.synthetic_state(hm, p)
+        colptr, rows = lm_pattern(om.LM, om.nmdf)
+        return om, xms, cps, colptr, rows
+
+    om, xms, cps, colptr, rows = setup(17)
+    t0 = time.perf_counter()
+    om.calc_r_K_fast(xms, cps, 0.5, 0.5, colptr, rows, nthreads=cores, want_out=False)
+    rate = om.numel / (time.perf_counter() - t0)
+    n = int(min(160, max(17, np.sqrt(rate * target_s))))
+    if n >= 18:
+        n = max(n, 19)
+    om, xms, cps, colptr, rows = setup(n)
+    for _ in range(max(1, min(warmup, 2))):
+        om.calc_r_K_fast(xms, cps, 0.5, 0.5, colptr, rows, nthreads=cores, want_out=False)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        om.calc_r_K_fast(xms, cps, 0.5, 0.5, colptr, rows, nthreads=cores, want_out=False)
+        ts.append(time.perf_counter() - t0)
+    tot = sum(ts)
+    return {"value": om.numel * steps / tot / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n}x{n}-element F_PULL {motion} patch ({om.numel} elements/step, {steps} steps, same "
+                      f"perturbed state generator), C++ restatement of the reference algorithm (complex-step tangent, "
+                      f"chunked std::thread tasks with private accumulators as FiniteElement.jl:88-147), "
+                      f"g++ -O2, {cores} threads; Julia itself is not installed"}, tot / steps * 1e3
+
+
+# ----------------------------------------------------------------------------------------------- main
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import __graft_entry__ as ge
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        ge.build()
+        cb, ms = cpu_reference_rate(a.motion, a.steps, a.warmup)
+        out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
+               "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"synthetic flat F_PULL patch, {a.motion}, bounded CPU sample (see cpu_baseline)"},
+               "cpu_baseline": cb,
+               "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "gpu_launches": 0}
+        print(json.dumps(out))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    import mafb200 as maf
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    motion = getattr(maf, a.motion)
+    p = maf.Params(motion=motion, scenario=maf.F_PULL, num1el=a.n, num2el=a.n, output=False)
+    t_setup = time.perf_counter()
+    mesh = maf.Mesh(p, pull_speed=0.5)
+    xms, cps = maf.synthetic_state(mesh, p)
+    asm = maf.Assembler(mesh, p, device=local_rank)
+    t_setup = time.perf_counter() - t_setup
+    mode = maf.SCATTER_ATOMIC if a.scatter == "atomic" else maf.SCATTER_DETERMINISTIC
+    dt = 0.5
+
+    # strips of element rows
+    if world > 1:
+        r0 = (rank * a.n) // world
+        r1 = ((rank + 1) * a.n) // world
+        asm.set_element_range(r0 * a.n + 1, r1 * a.n)
+    info = asm.range_info()
+    my_elems = info["elements"][1] - info["elements"][0] + 1
+
+    d_x = torch.from_numpy(np.ascontiguousarray(xms.T)).to(dev)
+    d_c = torch.from_numpy(np.ascontiguousarray(cps.T)).to(dev)
+    d_r = torch.zeros(mesh.nmdf, dtype=torch.float64, device=dev)
+    d_k = torch.zeros(asm.nnz, dtype=torch.float64, device=dev)
+    d_n = torch.zeros(1, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # interface overlaps with the neighbouring strips (1-based inclusive -> python slices)
+    nbrs = []
+    if world > 1:
+        mine = torch.tensor([info["rows"][0], info["rows"][1], info["slots"][0], info["slots"][1]], device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = [t.tolist() for t in allr]
+        for nb in (rank - 1, rank + 1):
+            if 0 <= nb < world:
+                lo_r, hi_r = max(allr[rank][0], allr[nb][0]), min(allr[rank][1], allr[nb][1])
+                lo_s, hi_s = max(allr[rank][2], allr[nb][2]), min(allr[rank][3], allr[nb][3])
+                nr, ns = max(0, hi_r - lo_r + 1), max(0, hi_s - lo_s + 1)
+                nbrs.append((nb, slice(lo_r - 1, lo_r - 1 + nr), slice(lo_s - 1, lo_s - 1 + ns),
+                             torch.empty(nr + ns, dtype=torch.float64, device=dev),
+                             torch.empty(nr + ns, dtype=torch.float64, device=dev)))
+        own_rows = slice(info["rows"][0] - 1 if rank == 0 else allr[rank - 1][1], info["rows"][1])
+
+    def step():
+        asm.assemble_device(d_x.data_ptr(), d_c.data_ptr(), dt, dt, scatter_mode=mode, d_r=d_r.data_ptr(),
+                            d_nzval=d_k.data_ptr(), d_rnorm2=d_n.data_ptr() if world == 1 else None, stream=stream)
+        if world > 1:
+            ops = []
+            for (nb, sr, sk, sbuf, rbuf) in nbrs:
+                nr = sr.stop - sr.start
+                sbuf[:nr].copy_(d_r[sr])
+                sbuf[nr:].copy_(d_k[sk])
+                ops.append(dist.P2POp(dist.isend, sbuf, nb))
+                ops.append(dist.P2POp(dist.irecv, rbuf, nb))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            for (nb, sr, sk, sbuf, rbuf) in nbrs:
+                nr = sr.stop - sr.start
+                d_r[sr] += rbuf[:nr]
+                d_k[sk] += rbuf[nr:]
+            d_n[0] = (d_r[own_rows] ** 2).sum()
+            dist.all_reduce(d_n)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = asm.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    ev0.record()
+    for _ in range(a.steps):
+        step()
+        kern_ms.append(asm.timings())
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = asm.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    clocks = sampler.stop() if rank == 0 else None
+    rnorm2 = float(d_n.item())
+    value = mesh.numel * a.steps / (ms * 1e-3) / 1e6
+
+    # ---- e2e through the host-buffer entry point (pinned host memory) ------------------------------------------
+    e2e = None
+    if not a.no_e2e and world == 1:
+        hx = torch.from_numpy(np.ascontiguousarray(xms.T)).pin_memory()
+        hc = torch.from_numpy(np.ascontiguousarray(cps.T)).pin_memory()
+        hr = torch.empty(mesh.nmdf, dtype=torch.float64).pin_memory()
+        hk = torch.empty(asm.nnz, dtype=torch.float64).pin_memory()
+        xs, cs = hx.numpy().T, hc.numpy().T          # column-major views for the ctypes call
+        for _ in range(max(1, a.warmup)):
+            asm.assemble(xs, cs, dt, dt, scatter_mode=mode, r=hr.numpy(), nzval=hk.numpy())
+        tot = 0.0
+        for _ in range(a.steps):
+            asm.assemble(xs, cs, dt, dt, scatter_mode=mode, r=hr.numpy(), nzval=hk.numpy())
+            tot += asm.timings()["total_ms"]
+        tm = asm.timings()
+        e2e = {"value": mesh.numel * a.steps / (tot * 1e-3) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int((3 + mesh.ndf) * mesh.numnp * 8),
+               "d2h_bytes_per_step": int((mesh.nmdf + asm.nnz + 1) * 8),
+               "ms_per_step": tot / a.steps, "last_step_ms": tm,
+               "note": "maf_assemble with pinned host buffers: H2D xms+cps, kernels, D2H r + nzval (the K values "
+                       "the host solver needs) inside the timed region (CUDA events on the handle's stream)"}
+        err = float(np.abs(hr.numpy() - d_r.cpu().numpy()).max())
+        e2e["max_abs_diff_r_vs_device_path"] = err
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (area_kernel) ---------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    area = float(np.mean([k["area_ms"] for k in kern_ms]))
+    other = {k: float(np.mean([t[k] for t in kern_ms])) for k in ("zero_ms", "bdry_ms", "gather_ms")}
+    fp64_peak = maf.fp64_peak_tflops(local_rank)
+    ach_gbs = my_elems * B_EL[a.motion] / (area * 1e-3) / 1e9
+    ach_tf = my_elems * F_EL[a.motion] / (area * 1e-3) / 1e12
+    roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                "traffic": None, "kernel": f"area_kernel<{a.motion}>", "kernel_ms": area,
+                "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_element": B_EL[a.motion],
+                "fp64": {"achieved_tflops": ach_tf, "peak_tflops": fp64_peak, "frac": ach_tf / fp64_peak,
+                         "algorithmic_flop_per_element": F_EL[a.motion],
+                         "peak_source": "maf_fp64_peak DFMA microbenchmark, this run",
+                         "note": "the kernel is FP64 CUDA-core bound (arithmetic intensity ~32 FLOP/B vs machine "
+                                 "balance ~5); the HBM fraction above is the schema's headline, this is the binding one"},
+                "other_kernels_ms": other}
+
+    cpu = None
+    if not a.no_cpu and world == 1:
+        cpu, _ = cpu_reference_rate(a.motion, 4, 1)
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"synthetic flat F_PULL patch {a.n}x{a.n} = {mesh.numel} elements, {a.motion} "
+                                  f"(ndf {mesh.ndf}), perturbed state (SURVEY 8(d)5), uniform-knot... see knots",
+                      "knots": "reference rule (Mesh.jl:176-181): centre-refined knots for >= 18 elements/direction",
+                      "numel": mesh.numel, "numnp": mesh.numnp, "nmdf": mesh.nmdf, "nnz": asm.nnz,
+                      "pattern": "P_blk", "scatter": a.scatter, "elements_per_rank": my_elems,
+                      "l2": "no flush: each step streams r + nzval (%.1f GB) >> 126 MB L2" % (asm.nnz * 8 / 1e9),
+                      "parallelism": f"{world} strip(s) of element rows; NCCL send/recv of interface rows + all-reduce "
+                                     "of the residual norm" if world > 1 else "single GPU",
+                      "setup_s": t_setup, "kernel": asm.kernel_info()},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+           "rnorm2": rnorm2}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

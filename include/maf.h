@@ -125,21 +125,30 @@ int maf_device_buffers(maf_handle* h, double** d_xms, double** d_cps, double** d
 int maf_stream(maf_handle* h, void** stream);
 int maf_sync(maf_handle* h);
 
-/* Diagnostics: device-side time of the last maf_assemble (CUDA events on the handle's stream), ms:
- * out[0] h2d, out[1] zero+area kernel, out[2] boundary kernel, out[3] gather/reduce (deterministic path),
- * out[4] d2h, out[5] whole call. And the number of kernels this handle has launched so far. */
-int maf_timings(maf_handle* h, double* out6);
+/* Diagnostics: device-side times of the last assembly (CUDA events on the stream it ran on), ms:
+ * out[0] h2d copies, out[1] area kernel, out[2] boundary kernels, out[3] gather kernels (deterministic path),
+ * out[4] d2h copies, out[5] whole maf_assemble call, out[6] zero-fill of r / nzval. out[0], out[4], out[5] are
+ * only set by maf_assemble. And the number of kernels this handle has launched so far. */
+int maf_timings(maf_handle* h, double* out7);
 int maf_launch_count(maf_handle* h, int64_t* n);
 
 /* Area-element kernel configuration actually used: out[0] threads per CTA, out[1] elements per CTA,
  * out[2] dynamic shared memory bytes per CTA, out[3] resident CTAs per SM, out[4] SM count. */
 int maf_kernel_info(maf_handle* h, int64_t* out5);
 
-/* Multi-GPU (one process per GPU): restrict this handle to the elements [el_first, el_last] (1-based, inclusive;
- * a strip of element rows). Rows of r / entries of nzval that receive contributions from other ranks are the
- * interface set returned by maf_interface (slot indices into nzval and row indices into r, 1-based); the caller
- * reduces exactly those with its collective (NCCL). */
+/* Multi-GPU (one process per GPU, every process holds the same mesh tables): restrict this handle to the elements
+ * [el_first, el_last] (1-based, inclusive) -- contiguous element ids are strips of element rows (Mesh.jl:582-588).
+ * Because unknowns are numbered node-major (Mesh.jl:276-284) a strip touches one contiguous range of rows of r and
+ * one contiguous range of nzval; maf_range_info returns them (all 1-based, inclusive):
+ *   out[0..1] elements, out[2..3] nodes, out[4..5] rows of r, out[6..7] entries of nzval.
+ * Only those ranges are written by an assembly. The ranges of neighbouring strips overlap exactly in the interface
+ * rows/entries (the two node rows a quadratic strip boundary shares); the caller sums the overlaps with its
+ * collective (NCCL send/recv between neighbours) -- nothing else crosses GPUs. */
 int maf_set_element_range(maf_handle* h, int64_t el_first, int64_t el_last);
+int maf_range_info(maf_handle* h, int64_t* out8);
+
+/* Measured FP64 FMA throughput of the device (TFLOP/s): the denominator of the FP64 roofline fraction. */
+int maf_fp64_peak(int device, double* tflops);
 
 #ifdef __cplusplus
 }

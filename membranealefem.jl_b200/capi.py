@@ -43,7 +43,7 @@ _lib = None
 
 EXPORTS = ["maf_create", "maf_destroy", "maf_last_error", "maf_nnz", "maf_pattern", "maf_assemble",
            "maf_assemble_device", "maf_device_buffers", "maf_stream", "maf_sync", "maf_timings", "maf_launch_count",
-           "maf_kernel_info", "maf_set_element_range"]
+           "maf_kernel_info", "maf_set_element_range", "maf_range_info", "maf_fp64_peak"]
 
 
 def load_library(path=None):
@@ -73,6 +73,8 @@ def load_library(path=None):
     L.maf_launch_count.argtypes = [C.c_void_p, _I64P]
     L.maf_kernel_info.argtypes = [C.c_void_p, _I64P]
     L.maf_set_element_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    L.maf_range_info.argtypes = [C.c_void_p, _I64P]
+    L.maf_fp64_peak.argtypes = [C.c_int, _F64P]
     if path == LIB_PATH:
         _lib = L
     return L
@@ -196,9 +198,9 @@ class Assembler:
         self._check(self.L.maf_sync(self.h))
 
     def timings(self):
-        o = np.zeros(6)
+        o = np.zeros(7)
         self._check(self.L.maf_timings(self.h, _ptr(o, C.c_double)))
-        return dict(zip(["h2d_ms", "area_ms", "bdry_ms", "gather_ms", "d2h_ms", "total_ms"], o.tolist()))
+        return dict(zip(["h2d_ms", "area_ms", "bdry_ms", "gather_ms", "d2h_ms", "total_ms", "zero_ms"], o.tolist()))
 
     def launch_count(self):
         n = C.c_int64()
@@ -212,3 +214,19 @@ class Assembler:
 
     def set_element_range(self, el_first, el_last):
         self._check(self.L.maf_set_element_range(self.h, el_first, el_last))
+
+    def range_info(self):
+        """1-based inclusive ranges this handle's element range touches."""
+        o = np.zeros(8, dtype=np.int64)
+        self._check(self.L.maf_range_info(self.h, _ptr(o, C.c_int64)))
+        return {"elements": (int(o[0]), int(o[1])), "nodes": (int(o[2]), int(o[3])), "rows": (int(o[4]), int(o[5])),
+                "slots": (int(o[6]), int(o[7]))}
+
+
+def fp64_peak_tflops(device=-1):
+    """Measured DFMA throughput of the device (roofline denominator)."""
+    L = load_library()
+    t = C.c_double()
+    if L.maf_fp64_peak(device, C.byref(t)) != 0:
+        raise MafError(L.maf_last_error(None).decode())
+    return t.value

@@ -90,17 +90,30 @@ boundary_kernel(const __grid_constant__ Config cfg, const Tables T, const Bounda
 // Deterministic path (maf_gather.cuh): one thread per node pair / per residual row.
 __global__ void __launch_bounds__(128)
 gather_K_kernel(const __grid_constant__ Config cfg, const Tables T, const GatherTables G,
-                const double* __restrict__ kel, int nij, int64_t e0, int64_t e1, double* __restrict__ nzval) {
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < G.npairs;
+                const double* __restrict__ kel, int nij, int64_t e0, int64_t e1, int64_t p_lo, int64_t p_hi,
+                double* __restrict__ nzval) {
+  for (int64_t p = p_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < p_hi;
        p += (int64_t)gridDim.x * blockDim.x)
     gather_K_pair(p, cfg, T, G, kel, nij, e0, e1, nzval);
 }
 __global__ void __launch_bounds__(128)
 gather_r_kernel(const __grid_constant__ Config cfg, const Tables T, const GatherTables G,
-                const double* __restrict__ rel, int64_t e0, int64_t e1, double* __restrict__ r_gl) {
-  const int64_t n = T.numnp * cfg.ndf;
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+                const double* __restrict__ rel, int64_t e0, int64_t e1, int64_t k_lo, int64_t k_hi,
+                double* __restrict__ r_gl) {
+  for (int64_t k = k_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < k_hi;
+       k += (int64_t)gridDim.x * blockDim.x)
     gather_r_row(k, cfg, T, G, rel, e0, e1, r_gl);
+}
+
+// FP64 roofline denominator: independent DFMA chains, 8 per thread, no memory traffic.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int k = 0; k < iters; ++k) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 12345.678) out[0] = s;  // keeps the chains alive without a store in the common case
 }
 
 __global__ void __launch_bounds__(256) rnorm2_partial(const double* __restrict__ r, int64_t n, double* part) {
@@ -152,8 +165,11 @@ struct maf_handle {
   double *h_pin_in = nullptr, *h_pin_out = nullptr;  // pinned staging for the host-buffer entry point
   size_t pin_in_bytes = 0, pin_out_bytes = 0;
   int64_t e0 = 0, e1 = 0;  // element range [e0, e1) assembled by this handle
+  // what that range touches: nodes [node_lo, node_hi), equations [eq_lo, eq_hi), nnz slots [slot_lo, slot_hi)
+  int64_t node_lo = 0, node_hi = 0, eq_lo = 0, eq_hi = 0, slot_lo = 0, slot_hi = 0;
+  bool timed_valid = false;
   int64_t launches = 0;
-  float ms[6] = {0, 0, 0, 0, 0, 0};
+  float ms[7] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 static std::string g_create_err;
@@ -190,6 +206,27 @@ static area_fn area_kernel_of(int motion) {
     case M_ALEV: return area_kernel<M_ALEV>;
     default: return area_kernel<M_ALEVB>;
   }
+}
+
+// what the element range [e0, e1) touches: node, equation and nnz-slot ranges (each contiguous)
+static void compute_ranges(maf_handle* h) {
+  const HostModel& M = h->M;
+  int64_t lo = M.numnp, hi = -1;
+  for (int64_t k = 9 * h->e0; k < 9 * h->e1; ++k) {
+    lo = std::min<int64_t>(lo, M.IX0[k]);
+    hi = std::max<int64_t>(hi, M.IX0[k]);
+  }
+  if (hi < 0) { lo = 0; hi = -1; }
+  h->node_lo = lo;
+  h->node_hi = hi + 1;
+  int64_t eq_lo = M.nmdf, eq_hi = 0;
+  for (int64_t k = lo * M.ndf; k < (hi + 1) * M.ndf; ++k)
+    if (M.ID0[k] >= 0) { eq_lo = std::min<int64_t>(eq_lo, M.ID0[k]); eq_hi = std::max<int64_t>(eq_hi, M.ID0[k] + 1); }
+  if (eq_hi <= eq_lo) eq_lo = eq_hi = 0;
+  h->eq_lo = eq_lo;
+  h->eq_hi = eq_hi;
+  h->slot_lo = M.sym.colptr[eq_lo];
+  h->slot_hi = M.sym.colptr[eq_hi];
 }
 
 static void ensure_gather(maf_handle* h) {
@@ -241,31 +278,37 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
   area_fn kern = area_kernel_of(M.motion);
   const int64_t ne = h->e1 - h->e0;
   const int grid = (int)std::min<int64_t>(std::max<int64_t>(ne, 1), (int64_t)h->grid);
-  if (timed) CU(cudaEventRecord(h->ev[1], s));
+  (void)timed;
+  h->timed_valid = false;
+  CU(cudaEventRecord(h->ev[1], s));
   StageSink st{nullptr, nullptr, nullptr, 0};
   if (mode == MAF_SCATTER_ATOMIC) {
-    CU(cudaMemsetAsync(d_r, 0, sizeof(double) * (size_t)M.nmdf, s));
-    CU(cudaMemsetAsync(d_nz, 0, sizeof(double) * (size_t)M.sym.nnz, s));
+    // only what this element range touches (contiguous, because unknowns are numbered node-major)
+    CU(cudaMemsetAsync(d_r + h->eq_lo, 0, sizeof(double) * (size_t)(h->eq_hi - h->eq_lo), s));
+    CU(cudaMemsetAsync(d_nz + h->slot_lo, 0, sizeof(double) * (size_t)(h->slot_hi - h->slot_lo), s));
   } else {
     ensure_gather(h);
     ensure_stage(h);
     st = StageSink{h->d_kel, h->d_rel, h->d_task_ij, h->nij};
   }
+  CU(cudaEventRecord(h->ev[6], s));
   if (ne > 0) {
     kern<<<grid, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, h->e0, h->e1);
     CU(cudaGetLastError());
     h->launches += 1;
   }
-  if (timed) CU(cudaEventRecord(h->ev[2], s));
+  CU(cudaEventRecord(h->ev[2], s));
   if (mode == MAF_SCATTER_DETERMINISTIC) {
     const int gb = h->sm_count * 16;
-    gather_K_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, h->G, h->d_kel, h->nij, h->e0, h->e1, d_nz);
+    const int64_t p_lo = M.sym.nbr_ptr[h->node_lo], p_hi = M.sym.nbr_ptr[h->node_hi];
+    gather_K_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, h->G, h->d_kel, h->nij, h->e0, h->e1, p_lo, p_hi, d_nz);
     CU(cudaGetLastError());
-    gather_r_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, h->G, h->d_rel, h->e0, h->e1, d_r);
+    gather_r_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, h->G, h->d_rel, h->e0, h->e1, h->node_lo * M.ndf,
+                                       h->node_hi * M.ndf, d_r);
     CU(cudaGetLastError());
     h->launches += 2;
   }
-  if (timed) CU(cudaEventRecord(h->ev[3], s));
+  CU(cudaEventRecord(h->ev[3], s));
   for (int bc = 0; bc < M.n_neu; ++bc) {
     const int n = M.b_offs[bc + 1] - M.b_offs[bc];
     if (n == 0) continue;
@@ -284,7 +327,8 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
       }
     }
   }
-  if (timed) CU(cudaEventRecord(h->ev[4], s));
+  CU(cudaEventRecord(h->ev[4], s));
+  h->timed_valid = true;
   if (d_rn) {
     rnorm2_partial<<<256, 256, 0, s>>>(d_r, M.nmdf, h->d_part);
     rnorm2_final<<<1, 256, 0, s>>>(h->d_part, 256, d_rn);
@@ -346,6 +390,7 @@ int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* pa
     HostModel& M = h->M;
     h->e0 = 0;
     h->e1 = M.numel;
+    compute_ranges(h);
 
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (int k = 0; k < 8; ++k) CU(cudaEventCreate(&h->ev[k]));
@@ -462,9 +507,6 @@ int maf_assemble(maf_handle* h, const double* xms, const double* cps, double tim
   CU(cudaEventRecord(h->ev[5], s));
   CU(cudaStreamSynchronize(s));
   CU(cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]));
-  CU(cudaEventElapsedTime(&h->ms[1], h->ev[1], h->ev[2]));
-  CU(cudaEventElapsedTime(&h->ms[3], h->ev[2], h->ev[3]));
-  CU(cudaEventElapsedTime(&h->ms[2], h->ev[3], h->ev[4]));
   CU(cudaEventElapsedTime(&h->ms[4], h->ev[4], h->ev[5]));
   CU(cudaEventElapsedTime(&h->ms[5], h->ev[0], h->ev[5]));
   MAF_API_END(h)
@@ -504,10 +546,17 @@ int maf_sync(maf_handle* h) {
   MAF_API_END(h)
 }
 
-int maf_timings(maf_handle* h, double* out6) {
+int maf_timings(maf_handle* h, double* out7) {
   MAF_API_BEGIN(h)
-  if (!out6) throw std::runtime_error("null output pointer");
-  for (int k = 0; k < 6; ++k) out6[k] = h->ms[k];
+  if (!out7) throw std::runtime_error("null output pointer");
+  if (h->timed_valid) {  // events of the last assembly, whichever entry point and stream launched it
+    CU(cudaEventSynchronize(h->ev[4]));
+    CU(cudaEventElapsedTime(&h->ms[6], h->ev[1], h->ev[6]));
+    CU(cudaEventElapsedTime(&h->ms[1], h->ev[6], h->ev[2]));
+    CU(cudaEventElapsedTime(&h->ms[3], h->ev[2], h->ev[3]));
+    CU(cudaEventElapsedTime(&h->ms[2], h->ev[3], h->ev[4]));
+  }
+  for (int k = 0; k < 7; ++k) out7[k] = h->ms[k];
   MAF_API_END(h)
 }
 
@@ -531,7 +580,55 @@ int maf_set_element_range(maf_handle* h, int64_t el_first, int64_t el_last) {
     throw std::runtime_error("element range outside 1..numel");
   h->e0 = el_first - 1;
   h->e1 = el_last;
+  compute_ranges(h);
   MAF_API_END(h)
+}
+
+int maf_range_info(maf_handle* h, int64_t* out8) {
+  MAF_API_BEGIN(h)
+  if (!out8) throw std::runtime_error("null output pointer");
+  out8[0] = h->e0 + 1; out8[1] = h->e1;              // elements, 1-based inclusive
+  out8[2] = h->node_lo + 1; out8[3] = h->node_hi;    // nodes touched
+  out8[4] = h->eq_lo + 1; out8[5] = h->eq_hi;        // rows of r touched
+  out8[6] = h->slot_lo + 1; out8[7] = h->slot_hi;    // entries of nzval touched
+  MAF_API_END(h)
+}
+
+int maf_fp64_peak(int device, double* tflops) {
+  try {
+    if (!tflops) return 1;
+    int dev = device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    double* d = nullptr;
+    CU(cudaMalloc(&d, 8));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    const int iters = 1 << 14, grid = prop.multiProcessorCount * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+      CU(cudaEventRecord(a, 0));
+      dfma_peak_kernel<<<grid, 256>>>(d, iters, 0.999999, 1e-9);
+      CU(cudaEventRecord(b, 0));
+      CU(cudaEventSynchronize(b));
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, a, b));
+      const double tf = 2.0 * 8.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+      if (rep > 0) best = std::max(best, tf);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
+    return 0;
+  } catch (std::exception& e) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_create_err = e.what();
+    return 2;
+  }
 }
 
 }  // extern "C"
