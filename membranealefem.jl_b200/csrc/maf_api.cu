@@ -24,6 +24,9 @@
 using namespace maf;
 
 #define MAF_NT 128  // threads per CTA of the area kernel (one element per CTA iteration)
+#ifndef MAF_MIN_CTAS
+#define MAF_MIN_CTAS 3  // resident CTAs per SM the register allocation is capped for
+#endif
 
 static_assert(sizeof(Config) <= 4000, "Config must fit the kernel parameter space");
 
@@ -38,7 +41,7 @@ struct StageSink {      // deterministic path staging buffers (NULL = atomics pa
 };
 
 template <int MOTION>
-__global__ void __launch_bounds__(MAF_NT)
+__global__ void __launch_bounds__(MAF_NT, MAF_MIN_CTAS)
 area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __restrict__ xms,
             const double* __restrict__ cps, double dt, double* __restrict__ r_gl, double* __restrict__ nzval,
             const StageSink st, int64_t e0, int64_t e1) {
@@ -430,6 +433,7 @@ int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* pa
     if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
       throw std::runtime_error("element needs more shared memory than the device offers");
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int nb = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, MAF_NT, h->smem_bytes));
     if (nb < 1) throw std::runtime_error("area kernel does not fit on an SM");

@@ -110,7 +110,8 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   std::vector<int> order(cfg.nblocks);
   for (int k = 0; k < cfg.nblocks; ++k) order[k] = k;
   std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-    return kind_cost(cfg.blocks[x].kind) > kind_cost(cfg.blocks[y].kind);
+    const int cx = kind_cost(cfg.blocks[x].kind), cy = kind_cost(cfg.blocks[y].kind);
+    return cx != cy ? cx > cy : cfg.blocks[x].kind < cfg.blocks[y].kind;
   });
   for (int k : order) {
     const Block& b = cfg.blocks[k];
@@ -142,14 +143,60 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   cfg.nitems = (int)items.size();
   for (int k = 0; k < cfg.nitems; ++k) cfg.items[k] = items[k];
 
-  // thread -> work maps
-  auto fill = [&](int n, int16_t* slot, int& rounds) {
-    rounds = (n + nthreads - 1) / nthreads;
+  // thread -> work maps. Work of one class (item type / block kind) shares a code path, so every class is cut
+  // into warp-sized chunks and each chunk is given to the least-loaded warp (longest-processing-time first):
+  // the lanes of a warp never diverge on the class, and the warps of the CTA finish at about the same time.
+  const int nwarps = nthreads / 32;
+  auto schedule = [&](const std::vector<int>& cls, const std::vector<int>& cost, int16_t* slot, int& rounds) {
+    struct Chunk { int cost; std::vector<int> ids; };
+    std::vector<Chunk> chunks;
+    for (size_t k = 0; k < cls.size();) {
+      size_t e = k;
+      while (e < cls.size() && cls[e] == cls[k]) ++e;
+      const int n = (int)(e - k), parts = (n + 31) / 32, per = (n + parts - 1) / parts;
+      for (int q = 0; q < parts; ++q) {
+        Chunk ch;
+        ch.cost = cost[k];
+        for (size_t t = k + (size_t)q * per; t < std::min(e, k + (size_t)(q + 1) * per); ++t) ch.ids.push_back((int)t);
+        chunks.push_back(ch);
+      }
+      k = e;
+    }
+    std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& x, const Chunk& y) { return x.cost > y.cost; });
+    std::vector<int> load(nwarps, 0);
+    std::vector<std::vector<const Chunk*>> plan(nwarps);
+    for (const Chunk& ch : chunks) {
+      int wbest = 0;
+      for (int w = 1; w < nwarps; ++w)
+        if (load[w] < load[wbest]) wbest = w;
+      plan[wbest].push_back(&ch);
+      load[wbest] += ch.cost;
+    }
+    rounds = 0;
+    for (int w = 0; w < nwarps; ++w) rounds = std::max(rounds, (int)plan[w].size());
     if (rounds * nthreads > MAF_MAX_SLOTS) throw std::runtime_error("slot table overflow");
-    for (int s = 0; s < rounds * nthreads; ++s) slot[s] = (int16_t)(s < n ? s : -1);
+    for (int s2 = 0; s2 < rounds * nthreads; ++s2) slot[s2] = -1;
+    for (int w = 0; w < nwarps; ++w)
+      for (size_t r = 0; r < plan[w].size(); ++r)
+        for (size_t l = 0; l < plan[w][r]->ids.size(); ++l)
+          slot[r * nthreads + w * 32 + l] = (int16_t)plan[w][r]->ids[l];
   };
-  fill(cfg.nitems, cfg.item_slot, cfg.item_rounds);
-  fill(cfg.ntasks, cfg.task_slot, cfg.task_rounds);
+  {
+    std::vector<int> cls(cfg.nitems), cost(cfg.nitems);
+    for (int k = 0; k < cfg.nitems; ++k) {
+      cls[k] = cfg.items[k].type;
+      cost[k] = cfg.items[k].type == IT_LIN ? 6 : 10;
+    }
+    schedule(cls, cost, cfg.item_slot, cfg.item_rounds);
+  }
+  {
+    std::vector<int> cls(cfg.ntasks), cost(cfg.ntasks);
+    for (int k = 0; k < cfg.ntasks; ++k) {
+      cls[k] = cfg.blocks[cfg.tasks[k].blk].kind;
+      cost[k] = kind_cost(cls[k]);
+    }
+    schedule(cls, cost, cfg.task_slot, cfg.task_rounds);
+  }
 
   // rows present in the pattern of a column of dof J
   for (int J = 0; J < 8; ++J) cfg.rowmask[J] = 0;

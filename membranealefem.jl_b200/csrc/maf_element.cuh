@@ -177,22 +177,49 @@ MAF_HD int a_index(const Config& cfg, int f, int i, int c, int g, int j, int d) 
   return cfg.aoff[f] + (i * cfg.rnc[f] + (c - cfg.rc0[f])) * cfg.ald[f] + cfg.coloff[f][g] + j * cfg.cnc[f][g] +
          (d - cfg.cd0[f][g]);
 }
+// does row field f keep a column for trial (g, ., d)?
+MAF_HD bool has_col(const Config& cfg, int f, int g, int d) {
+  return cfg.coloff[f][g] >= 0 && d >= cfg.cd0[f][g] && d < cfg.cd0[f][g] + cfg.cnc[f][g];
+}
 
-// store one tangent column (direction = trial (g, j, d)) for every row field that has a (f,g) block containing d
+// store one tangent column (direction = trial (g, j, d)) for every row field that has a (f,g) block containing d.
+// All indices into S are compile-time (full unroll) so that S lives in registers.
 template <class T>
 MAF_HD void store_column(const Config& cfg, double* Agp, double w, const GpStress<T>& S, int g, int j, int d) {
+  if (has_col(cfg, F_V, g, d)) {
+    const int base = a_index(cfg, F_V, 0, cfg.rc0[F_V], g, j, d), ld = cfg.ald[F_V], nr = cfg.rnc[F_V], c0 = cfg.rc0[F_V];
 #pragma unroll
-  for (int f = 0; f < NFIELD; ++f) {
-    if (cfg.coloff[f][g] < 0) continue;
-    if (d < cfg.cd0[f][g] || d >= cfg.cd0[f][g] + cfg.cnc[f][g]) continue;
-    if (f == F_V || f == F_M) {
-      for (int i = 0; i < 3; ++i)
-        for (int c = cfg.rc0[f]; c < cfg.rc0[f] + cfg.rnc[f]; ++c)
-          Agp[a_index(cfg, f, i, c, g, j, d)] = w * der(f == F_V ? S.Sv[c][i] : S.Sm[c][i]);
-    } else {
-      Agp[a_index(cfg, f, 0, CH_N, g, j, d)] = w * der(f == F_L ? S.Sl : S.Sp);
-    }
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if (c >= c0 && c < c0 + nr) Agp[base + (i * nr + (c - c0)) * ld] = w * der(S.Sv[c][i]);
   }
+  if (has_col(cfg, F_M, g, d)) {
+    const int base = a_index(cfg, F_M, 0, cfg.rc0[F_M], g, j, d), ld = cfg.ald[F_M], nr = cfg.rnc[F_M], c0 = cfg.rc0[F_M];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if (c >= c0 && c < c0 + nr) Agp[base + (i * nr + (c - c0)) * ld] = w * der(S.Sm[c][i]);
+  }
+  if (has_col(cfg, F_L, g, d)) Agp[a_index(cfg, F_L, 0, CH_N, g, j, d)] = w * der(S.Sl);
+  if (has_col(cfg, F_P, g, d)) Agp[a_index(cfg, F_P, 0, CH_N, g, j, d)] = w * der(S.Sp);
+}
+
+// zero-fill one column (used before the closed-form columns, which touch only a few rows)
+MAF_HD void zero_column(const Config& cfg, double* Agp, int g, int j, int d) {
+  for (int f = 0; f < 2; ++f) {
+    if (!has_col(cfg, f, g, d)) continue;
+    const int base = a_index(cfg, f, 0, cfg.rc0[f], g, j, d), ld = cfg.ald[f], nrow = 3 * cfg.rnc[f];
+    for (int r = 0; r < nrow; ++r) Agp[base + r * ld] = 0.0;
+  }
+  if (has_col(cfg, F_L, g, d)) Agp[a_index(cfg, F_L, 0, CH_N, g, j, d)] = 0.0;
+  if (has_col(cfg, F_P, g, d)) Agp[a_index(cfg, F_P, 0, CH_N, g, j, d)] = 0.0;
+}
+// write one entry of a closed-form column if the row (f, i, c) is stored
+MAF_HD void put(const Config& cfg, double* Agp, int f, int i, int c, int g, int j, int d, double val) {
+  if (has_col(cfg, f, g, d) && c >= cfg.rc0[f] && c < cfg.rc0[f] + cfg.rnc[f])
+    Agp[a_index(cfg, f, i, c, g, j, d)] = val;
 }
 
 MAF_HD void load_E(const double* E, double a[2][3], double c[3][3], double dv[2][3], double v[3], double dm[2][3],
@@ -211,10 +238,14 @@ MAF_HD void load_E(const double* E, double a[2][3], double c[3][3], double dv[2]
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Phase 2: Gauss-point tangent A[gp] (exact derivative) and primal S[gp].
-//  IT_GEO_A (gamma, j): direction d x_{,gamma}_j = dt, d (mesh velocity)_{,gamma}_j = 1  -> column (mesh, j, N_gamma)
-//  IT_GEO_B           : directions d x_{,k}_j = dt for the three second derivatives      -> columns (mesh, j, N_k)
-//  IT_LIN             : primal S, and the closed-form columns of the dofs that do not move the mesh
+// Phase 2: Gauss-point tangent A[gp] (exact derivative) and primal S[gp]. Work items of one Gauss point:
+//  IT_GEO_A (gamma, j): forward-mode direction  d x_{,gamma}_j = dt, d (mesh velocity)_{,gamma}_j = 1
+//                       -> column (mesh dof j, N_gamma): the merged d/dcps + dt d/dx of FiniteElement.jl:113-123
+//  IT_GEO_B           : columns (mesh dof j, N_k), k = 11,22,12. x_{,k} enters only through b_k = x_{,k}.n and
+//                       Gamma^mu_k = x_{,k}.a^mu, so  dS/dx_{,k}_j = dS/db_k n_j + dS/dGamma^mu_k a^mu_j : three
+//                       forward-mode b-directions + the closed-form Gamma term (-Q_k a^mu_j on the N_mu rows)
+//  IT_LIN             : primal S (residual), and the closed-form columns of the dofs that do not move the mesh
+//                       (the residual is affine in cps at fixed x)
 // ---------------------------------------------------------------------------------------------------------
 template <int MOTION>
 MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, double* sm) {
@@ -225,6 +256,7 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, double
   double a[2][3], c[3][3], dv[2][3], v[3], dm[2][3], vm[3], lam, pm;
   load_E(E, a, c, dv, v, dm, vm, lam, pm);
   const int mf = cfg.mesh_field;
+  constexpr bool ALE = (MOTION == M_ALEV || MOTION == M_ALEVB);
 
   if (it.type == IT_GEO_A) {
     Dual ad[2][3];
@@ -251,77 +283,130 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, double
       gp_eval<MOTION, Dual, double, double, Dual, double>(ad, c, dv, v, dmd, vmd, lam, pm, cfg.mat, S);
     }
     store_column(cfg, Agp, w, S, mf, it.j, CH_N1 + it.gamma);
-  } else if (it.type == IT_GEO_B) {
-    for (int k = 0; k < 3; ++k)
+    return;
+  }
+
+  GpGeom<double> g;
+  gp_geom(a, g);
+  double b[3], Gam[3][2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    b[k] = c[k][0] * g.n[0] + c[k][1] * g.n[1] + c[k][2] * g.n[2];
+#pragma unroll
+    for (int mu = 0; mu < 2; ++mu) Gam[k][mu] = c[k][0] * g.up[mu][0] + c[k][1] * g.up[mu][1] + c[k][2] * g.up[mu][2];
+  }
+
+  if (it.type == IT_GEO_B) {
+    const bool mrows = (MOTION == M_ALEVB);  // the mesh rows carry the bending moment only for ALEVB
+    for (int k = 0; k < 3; ++k) {
+      Dual bd[3] = {Dual(b[0], k == 0 ? 1.0 : 0.0), Dual(b[1], k == 1 ? 1.0 : 0.0), Dual(b[2], k == 2 ? 1.0 : 0.0)};
+      GpStress<Dual> S;
+      gp_core<MOTION>(g, a, bd, Gam, dv, v, dm, vm, lam, pm, cfg.mat, S);
+      // Q_k[i] = J M~^k n_i is the primal N_k row of the velocity equations
+      double Qk[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        Qk[i] = k == 0 ? S.Sv[CH_N11][i].v : (k == 1 ? S.Sv[CH_N22][i].v : S.Sv[CH_N12][i].v);
+      const double wdt = w * dt;
+#pragma unroll
       for (int j = 0; j < 3; ++j) {
-        Dual cd[3][3];
+        const int d = CH_N11 + k;
+        const double nj = g.n[j], u0 = g.up[0][j], u1 = g.up[1][j];
+        if (has_col(cfg, F_V, mf, d)) {
+          const int base = a_index(cfg, F_V, 0, cfg.rc0[F_V], mf, j, d), ld = cfg.ald[F_V], nr = cfg.rnc[F_V],
+                    c0 = cfg.rc0[F_V];
 #pragma unroll
-        for (int kk = 0; kk < 3; ++kk)
+          for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int i = 0; i < 3; ++i) cd[kk][i] = Dual(c[kk][i], (kk == k && i == j) ? dt : 0.0);
-        GpStress<Dual> S;
-        gp_eval<MOTION, double, Dual, double, double, double>(a, cd, dv, v, dm, vm, lam, pm, cfg.mat, S);
-        store_column(cfg, Agp, w, S, mf, j, CH_N11 + k);
+            for (int cc = 0; cc < NCH; ++cc) {
+              if (cc < c0 || cc >= c0 + nr) continue;
+              double val = S.Sv[cc][i].d * nj;
+              if (cc == CH_N1) val -= Qk[i] * u0;
+              if (cc == CH_N2) val -= Qk[i] * u1;
+              Agp[base + (i * nr + (cc - c0)) * ld] = wdt * val;
+            }
+        }
+        if (has_col(cfg, F_M, mf, d)) {
+          const int base = a_index(cfg, F_M, 0, cfg.rc0[F_M], mf, j, d), ld = cfg.ald[F_M], nr = cfg.rnc[F_M],
+                    c0 = cfg.rc0[F_M];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int cc = 0; cc < NCH; ++cc) {
+              if (cc < c0 || cc >= c0 + nr) continue;
+              double val = S.Sm[cc][i].d * nj;
+              if (mrows && cc == CH_N1) val -= Qk[i] * u0;
+              if (mrows && cc == CH_N2) val -= Qk[i] * u1;
+              Agp[base + (i * nr + (cc - c0)) * ld] = wdt * val;
+            }
+        }
+        // the lambda and pm rows do not depend on the second derivatives of x
+        if (has_col(cfg, F_L, mf, d)) Agp[a_index(cfg, F_L, 0, CH_N, mf, j, d)] = 0.0;
+        if (has_col(cfg, F_P, mf, d)) Agp[a_index(cfg, F_P, 0, CH_N, mf, j, d)] = 0.0;
       }
-  } else {
-    // primal stresses -> S[gp]
-    GpStress<double> S;
-    gp_eval<MOTION, double, double, double, double, double>(a, c, dv, v, dm, vm, lam, pm, cfg.mat, S);
-    double* Sg = sm + cfg.o_S + S_STRIDE * gp;
+    }
+    return;
+  }
+
+  // ---- IT_LIN: primal stresses -> S[gp] ----
+  GpStress<double> S;
+  gp_core<MOTION>(g, a, b, Gam, dv, v, dm, vm, lam, pm, cfg.mat, S);
+  double* Sg = sm + cfg.o_S + S_STRIDE * gp;
 #pragma unroll
-    for (int cc = 0; cc < NCH; ++cc)
+  for (int cc = 0; cc < NCH; ++cc)
 #pragma unroll
-      for (int i = 0; i < 3; ++i) { Sg[S_V + 3 * cc + i] = S.Sv[cc][i]; Sg[S_M + 3 * cc + i] = S.Sm[cc][i]; }
-    Sg[S_L] = S.Sl;
-    Sg[S_P] = S.Sp;
-    // closed-form columns of the dofs that do not move the mesh (the residual is affine in cps at fixed x)
-    for (int j = 0; j < 3; ++j) {
-      if (mf != F_V) {  // velocity gradient channels (v, j, N_mu), mu = 1,2 : viscous tangent + incompressibility
-        for (int mu = 0; mu < 2; ++mu) {
-          Dual dvd[2][3];
+    for (int i = 0; i < 3; ++i) { Sg[S_V + 3 * cc + i] = S.Sv[cc][i]; Sg[S_M + 3 * cc + i] = S.Sm[cc][i]; }
+  Sg[S_L] = S.Sl;
+  Sg[S_P] = S.Sp;
+  // ---- closed-form columns (all factors below are metric quantities of this Gauss point) ----
+  const double wJ = w * g.J, zv = cfg.mat.zv, am = cfg.mat.am, kdb = cfg.mat.adb / cfg.mat.zv;
+  const double Aup[2][2] = {{g.A11, g.A12}, {g.A12, g.A22}};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (mf != F_V) {
+      // (v, j, N_mu): d pi^{ab}/d v_{,mu}_j = zv (a^a_j a^{mu b} + a^b_j a^{mu a})   =>
+      //   d Sv[N_al][i] = J zv (a^al_j a^mu_i + a^{mu al} (delta_ij - n_i n_j)),   d Sl = J a^mu_j
+#pragma unroll
+      for (int mu = 0; mu < 2; ++mu) {
+        const int d = CH_N1 + mu;
+        zero_column(cfg, Agp, F_V, j, d);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double Pij = (i == j ? 1.0 : 0.0) - g.n[i] * g.n[j];
 #pragma unroll
           for (int al = 0; al < 2; ++al)
-#pragma unroll
-            for (int i = 0; i < 3; ++i) dvd[al][i] = Dual(dv[al][i], (al == mu && i == j) ? 1.0 : 0.0);
-          Dual vd[3] = {Dual(v[0]), Dual(v[1]), Dual(v[2])};
-          GpStress<Dual> Sd;
-          gp_eval<MOTION, double, double, Dual, double, double>(a, c, dvd, vd, dm, vm, lam, pm, cfg.mat, Sd);
-          store_column(cfg, Agp, w, Sd, F_V, j, CH_N1 + mu);
+            put(cfg, Agp, F_V, i, CH_N1 + al, F_V, j, d, wJ * zv * (g.up[al][j] * g.up[mu][i] + Aup[mu][al] * Pij));
         }
-        if (MOTION == M_EUL || MOTION == M_ALEV || MOTION == M_ALEVB) {  // value channel (v, j, N)
-          Dual dvd[2][3];
-#pragma unroll
-          for (int al = 0; al < 2; ++al)
-#pragma unroll
-            for (int i = 0; i < 3; ++i) dvd[al][i] = Dual(dv[al][i]);
-          Dual vd[3] = {Dual(v[0], j == 0 ? 1.0 : 0.0), Dual(v[1], j == 1 ? 1.0 : 0.0), Dual(v[2], j == 2 ? 1.0 : 0.0)};
-          GpStress<Dual> Sd;
-          gp_eval<MOTION, double, double, Dual, double, double>(a, c, dvd, vd, dm, vm, lam, pm, cfg.mat, Sd);
-          store_column(cfg, Agp, w, Sd, F_V, j, CH_N);
-        }
+        if (has_col(cfg, F_L, F_V, d)) Agp[a_index(cfg, F_L, 0, CH_N, F_V, j, d)] = wJ * g.up[mu][j];
       }
-      if (MOTION == M_EUL || MOTION == M_ALEV || MOTION == M_ALEVB) {  // (vm, j, N)
-        Dual dmd[2][3];
+      if (MOTION == M_EUL || ALE) {  // (v, j, N): EUL d Sm[N][i] = -am J n_i n_j ; ALE d Sp = +J n_j
+        zero_column(cfg, Agp, F_V, j, CH_N);
+        if (MOTION == M_EUL) {
 #pragma unroll
-        for (int al = 0; al < 2; ++al)
-#pragma unroll
-          for (int i = 0; i < 3; ++i) dmd[al][i] = Dual(dm[al][i]);
-        Dual vmd[3] = {Dual(vm[0], j == 0 ? 1.0 : 0.0), Dual(vm[1], j == 1 ? 1.0 : 0.0), Dual(vm[2], j == 2 ? 1.0 : 0.0)};
-        GpStress<Dual> Sd;
-        gp_eval<MOTION, double, double, double, Dual, double>(a, c, dv, v, dmd, vmd, lam, pm, cfg.mat, Sd);
-        store_column(cfg, Agp, w, Sd, F_M, j, CH_N);
+          for (int i = 0; i < 3; ++i) put(cfg, Agp, F_M, i, CH_N, F_V, j, CH_N, -wJ * am * g.n[i] * g.n[j]);
+        }
+        if (ALE && has_col(cfg, F_P, F_V, CH_N)) Agp[a_index(cfg, F_P, 0, CH_N, F_V, j, CH_N)] = wJ * g.n[j];
       }
     }
-    {  // (lambda, N)
-      GpStress<Dual> Sd;
-      gp_eval<MOTION, double, double, double, double, Dual>(a, c, dv, v, dm, vm, Dual(lam, 1.0), Dual(pm), cfg.mat, Sd);
-      store_column(cfg, Agp, w, Sd, F_L, 0, CH_N);
+    if (MOTION == M_EUL || ALE) {    // (vm, j, N): EUL d Sm[N][i] = am J delta_ij ; ALE d Sp = -J n_j
+      zero_column(cfg, Agp, F_M, j, CH_N);
+      if (MOTION == M_EUL) put(cfg, Agp, F_M, j, CH_N, F_M, j, CH_N, wJ * am);
+      if (ALE && has_col(cfg, F_P, F_M, CH_N)) Agp[a_index(cfg, F_P, 0, CH_N, F_M, j, CH_N)] = -wJ * g.n[j];
     }
-    if (MOTION == M_ALEV || MOTION == M_ALEVB) {  // (pm, N)
-      GpStress<Dual> Sd;
-      gp_eval<MOTION, double, double, double, double, Dual>(a, c, dv, v, dm, vm, Dual(lam), Dual(pm, 1.0), cfg.mat, Sd);
-      store_column(cfg, Agp, w, Sd, F_P, 0, CH_N);
-    }
+  }
+  {  // (lambda, N): d Sv[N_al][i] = J a^al_i ; d Sl = -adb/zv
+    zero_column(cfg, Agp, F_L, 0, CH_N);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int al = 0; al < 2; ++al) put(cfg, Agp, F_V, i, CH_N1 + al, F_L, 0, CH_N, wJ * g.up[al][i]);
+    if (has_col(cfg, F_L, F_L, CH_N)) Agp[a_index(cfg, F_L, 0, CH_N, F_L, 0, CH_N)] = -w * kdb;
+  }
+  if (ALE) {  // (pm, N): d Sm[N][i] = -J n_i ; d Sp = -adb/zv
+    zero_column(cfg, Agp, F_P, 0, CH_N);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) put(cfg, Agp, F_M, i, CH_N, F_P, 0, CH_N, -wJ * g.n[i]);
+    if (has_col(cfg, F_P, F_P, CH_N)) Agp[a_index(cfg, F_P, 0, CH_N, F_P, 0, CH_N)] = -w * kdb;
   }
 }
 

@@ -78,53 +78,56 @@ template <class T> struct GpStress {
   T Sl, Sp;
 };
 
-// Inputs at the Gauss point (all interpolated from nodal values with the basis table):
-//   a[al][i] = x_{,al} (GeoDynStress.jl:112), c[k][i] = x_{,11} x_{,22} x_{,12} (:115),
-//   dv[al][i] = v_{,al} (:136), v[i] (:135), dm[al][i] = vm_{,al} (:143), vm[i] (:142), lam (:139), pm (:140).
-template <int MOTION, class TA, class TC, class TV, class TM, class TS>
-MAF_HD void gp_eval(const TA a[2][3], const TC c[3][3], const TV dv[2][3], const TV v[3], const TM dm[2][3],
-                    const TM vm[3], TS lam, TS pm, const Material& mat,
-                    GpStress<typename Prom<typename Prom<typename Prom<TA, TC>::T, typename Prom<TV, TM>::T>::T, TS>::T>& out) {
-  typedef typename Prom<TA, TC>::T TG;                                   // curvature-dependent geometry
-  typedef typename Prom<typename Prom<typename Prom<TA, TC>::T, typename Prom<TV, TM>::T>::T, TS>::T TO;
-  typedef typename Prom<TA, TV>::T TPV;
-  typedef typename Prom<TA, TM>::T TPM;
+// Metric quantities that depend on the tangent vectors only (GeoDynStress.jl:117-123).
+template <class TA> struct GpGeom {
+  TA A11, A12, A22;   // a^{alpha beta}
+  TA idet, J, iJ;
+  TA up[2][3];        // a^alpha
+  TA n[3];            // unit normal
+};
 
-  // metric (GeoDynStress.jl:117-120)
+template <class TA> MAF_HD void gp_geom(const TA a[2][3], GpGeom<TA>& g) {
   TA a11 = a[0][0] * a[0][0] + a[0][1] * a[0][1] + a[0][2] * a[0][2];
   TA a12 = a[0][0] * a[1][0] + a[0][1] * a[1][1] + a[0][2] * a[1][2];
   TA a22 = a[1][0] * a[1][0] + a[1][1] * a[1][1] + a[1][2] * a[1][2];
   TA det = a11 * a22 - a12 * a12;
-  TA idet = 1.0 / det;
-  TA A11 = a22 * idet, A22 = a11 * idet, A12 = -(a12 * idet);
-  TA J = dsqrt(det);
-  TA iJ = 1.0 / J;
-  TA up[2][3];  // a^alpha (:119)
+  g.idet = 1.0 / det;
+  g.A11 = a22 * g.idet;
+  g.A22 = a11 * g.idet;
+  g.A12 = -(a12 * g.idet);
+  g.J = dsqrt(det);
+  g.iJ = 1.0 / g.J;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    up[0][i] = a[0][i] * A11 + a[1][i] * A12;
-    up[1][i] = a[0][i] * A12 + a[1][i] * A22;
+    g.up[0][i] = a[0][i] * g.A11 + a[1][i] * g.A12;
+    g.up[1][i] = a[0][i] * g.A12 + a[1][i] * g.A22;
   }
-  TA n[3];  // unit normal (:123)
-  n[0] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * iJ;
-  n[1] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * iJ;
-  n[2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * iJ;
+  g.n[0] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * g.iJ;
+  g.n[1] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * g.iJ;
+  g.n[2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * g.iJ;
+}
 
-  const bool bending_rows = true;  // Sv always carries the bending moment rows
-  TG b0 = c[0][0] * n[0] + c[0][1] * n[1] + c[0][2] * n[2];  // b_11 (:124-126)
-  TG b1 = c[1][0] * n[0] + c[1][1] * n[1] + c[1][2] * n[2];  // b_22
-  TG b2 = c[2][0] * n[0] + c[2][1] * n[1] + c[2][2] * n[2];  // b_12
+// Core of the Gauss-point evaluation. The second derivatives of x enter ONLY through the curvature components
+// b[k] = x_{,k} . n (k = 11, 22, 12; GeoDynStress.jl:124-126) and the Christoffel symbols
+// Gam[k][mu] = x_{,k} . a^mu (:121), which is what lets the tangent w.r.t. x_{,k} be assembled from three
+// b-directions plus a closed-form Gamma term (maf_element.cuh, IT_GEO_B).
+//   a[al][i] = x_{,al} (:112), dv[al][i] = v_{,al} (:136), v[i] (:135), dm[al][i] = vm_{,al} (:143), vm[i] (:142),
+//   lam (:139), pm (:140).
+template <int MOTION, class TA, class TB, class TGm, class TV, class TM, class TS, class TO>
+MAF_HD void gp_core(const GpGeom<TA>& g, const TA a[2][3], const TB b[3], const TGm Gam[3][2], const TV dv[2][3],
+                    const TV v[3], const TM dm[2][3], const TM vm[3], TS lam, TS pm, const Material& mat,
+                    GpStress<TO>& out) {
+  typedef typename Prom<TA, TB>::T TG;  // curvature-dependent geometry
+  typedef typename Prom<TA, TV>::T TPV;
+  typedef typename Prom<TA, TM>::T TPM;
+  const TA A11 = g.A11, A12 = g.A12, A22 = g.A22, J = g.J;
+  const TB b0 = b[0], b1 = b[1], b2 = b[2];
   // b^{alpha beta} = a^{..} b a^{..}  (:127)
   TG t11 = A11 * b0 + A12 * b2, t12 = A11 * b2 + A12 * b1;
   TG t21 = A12 * b0 + A22 * b2, t22 = A12 * b2 + A22 * b1;
   TG B11 = t11 * A11 + t12 * A12, B12 = t11 * A12 + t12 * A22, B22 = t21 * A12 + t22 * A22;
   TG H = 0.5 * (A11 * b0 + 2.0 * (A12 * b2) + A22 * b1);  // (:129)
-  TG Kg = (b0 * b1 - b2 * b2) * idet;                     // (:130)
-  TG Gam[3][2];                                           // Gamma^mu_k = x_{,k} . a^mu (:121)
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-#pragma unroll
-    for (int mu = 0; mu < 2; ++mu) Gam[k][mu] = c[k][0] * up[mu][0] + c[k][1] * up[mu][1] + c[k][2] * up[mu][2];
+  TG Kg = (b0 * b1 - b2 * b2) * g.idet;                   // (:130)
 
   // bending part of the in-plane stress and the moment (:150-154)
   TG bs = mat.kb * (H * H) - mat.kg * Kg;
@@ -140,15 +143,14 @@ MAF_HD void gp_eval(const TA a[2][3], const TC c[3][3], const TV dv[2][3], const
   for (int k = 0; k < 3; ++k) {
     TG jm = J * Mt[k];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) Q[k][i] = jm * n[i];
+    for (int i = 0; i < 3; ++i) Q[k][i] = jm * g.n[i];
   }
-  (void)bending_rows;
 
   // viscous stress pi^{ab} = zv (a^a . v_{,m} a^{mb} + a^b . v_{,m} a^{ma})  (:148-149)
-  TPV g00 = up[0][0] * dv[0][0] + up[0][1] * dv[0][1] + up[0][2] * dv[0][2];
-  TPV g01 = up[0][0] * dv[1][0] + up[0][1] * dv[1][1] + up[0][2] * dv[1][2];
-  TPV g10 = up[1][0] * dv[0][0] + up[1][1] * dv[0][1] + up[1][2] * dv[0][2];
-  TPV g11 = up[1][0] * dv[1][0] + up[1][1] * dv[1][1] + up[1][2] * dv[1][2];
+  TPV g00 = g.up[0][0] * dv[0][0] + g.up[0][1] * dv[0][1] + g.up[0][2] * dv[0][2];
+  TPV g01 = g.up[0][0] * dv[1][0] + g.up[0][1] * dv[1][1] + g.up[0][2] * dv[1][2];
+  TPV g10 = g.up[1][0] * dv[0][0] + g.up[1][1] * dv[0][1] + g.up[1][2] * dv[0][2];
+  TPV g11 = g.up[1][0] * dv[1][0] + g.up[1][1] * dv[1][1] + g.up[1][2] * dv[1][2];
   TPV p00 = g00 * A11 + g01 * A12, p01 = g00 * A12 + g01 * A22;
   TPV p10 = g10 * A11 + g11 * A12, p11 = g10 * A12 + g11 * A22;
   TPV pi11 = (2.0 * mat.zv) * p00, pi22 = (2.0 * mat.zv) * p11, pi12 = mat.zv * (p01 + p10);
@@ -168,7 +170,7 @@ MAF_HD void gp_eval(const TA a[2][3], const TC c[3][3], const TV dv[2][3], const
     out.Sv[CH_N11][i] = Q[0][i];
     out.Sv[CH_N22][i] = Q[1][i];
     out.Sv[CH_N12][i] = Q[2][i];
-    out.Sv[CH_N][i] = (-mat.pn) * (J * n[i]);
+    out.Sv[CH_N][i] = (-mat.pn) * (J * g.n[i]);
   }
   // ---- lambda row (:298-299) ----
   out.Sl = J * (g00 + g11) - (mat.adb / mat.zv) * lam;
@@ -180,14 +182,14 @@ MAF_HD void gp_eval(const TA a[2][3], const TC c[3][3], const TV dv[2][3], const
     for (int i = 0; i < 3; ++i) out.Sm[cch][i] = TO(0.0);
   out.Sp = TO(0.0);
   if (MOTION == M_EUL) {  // (:300-303)
-    TPV ndv = n[0] * v[0] + n[1] * v[1] + n[2] * v[2];
+    TPV ndv = g.n[0] * v[0] + g.n[1] * v[1] + g.n[2] * v[2];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) out.Sm[CH_N][i] = mat.am * (J * (vm[i] - n[i] * ndv));
+    for (int i = 0; i < 3; ++i) out.Sm[CH_N][i] = mat.am * (J * (vm[i] - g.n[i] * ndv));
   } else if (MOTION == M_ALEV || MOTION == M_ALEVB) {  // (:304-313), sigma^m at GeoDynStress.jl:156-159
-    TPM h00 = up[0][0] * dm[0][0] + up[0][1] * dm[0][1] + up[0][2] * dm[0][2];
-    TPM h01 = up[0][0] * dm[1][0] + up[0][1] * dm[1][1] + up[0][2] * dm[1][2];
-    TPM h10 = up[1][0] * dm[0][0] + up[1][1] * dm[0][1] + up[1][2] * dm[0][2];
-    TPM h11 = up[1][0] * dm[1][0] + up[1][1] * dm[1][1] + up[1][2] * dm[1][2];
+    TPM h00 = g.up[0][0] * dm[0][0] + g.up[0][1] * dm[0][1] + g.up[0][2] * dm[0][2];
+    TPM h01 = g.up[0][0] * dm[1][0] + g.up[0][1] * dm[1][1] + g.up[0][2] * dm[1][2];
+    TPM h10 = g.up[1][0] * dm[0][0] + g.up[1][1] * dm[0][1] + g.up[1][2] * dm[0][2];
+    TPM h11 = g.up[1][0] * dm[1][0] + g.up[1][1] * dm[1][1] + g.up[1][2] * dm[1][2];
     TPM q00 = h00 * A11 + h01 * A12, q01 = h00 * A12 + h01 * A22;
     TPM q10 = h10 * A11 + h11 * A12, q11 = h10 * A12 + h11 * A22;
     TO m11 = sb11 + (2.0 * mat.zv) * q00;
@@ -207,11 +209,29 @@ MAF_HD void gp_eval(const TA a[2][3], const TC c[3][3], const TV dv[2][3], const
         out.Sm[CH_N22][i] = Q[1][i];
         out.Sm[CH_N12][i] = Q[2][i];
       }
-      out.Sm[CH_N][i] = -(J * n[i]) * pm;
-      nd = nd + n[i] * (vm[i] - v[i]);
+      out.Sm[CH_N][i] = -(J * g.n[i]) * pm;
+      nd = nd + g.n[i] * (vm[i] - v[i]);
     }
     out.Sp = -(J * nd) - (mat.adb / mat.zv) * pm;
   }
+}
+
+// Full evaluation from the interpolated fields: c[k][i] = x_{,11} x_{,22} x_{,12} (GeoDynStress.jl:115).
+template <int MOTION, class TA, class TC, class TV, class TM, class TS>
+MAF_HD void gp_eval(const TA a[2][3], const TC c[3][3], const TV dv[2][3], const TV v[3], const TM dm[2][3],
+                    const TM vm[3], TS lam, TS pm, const Material& mat,
+                    GpStress<typename Prom<typename Prom<typename Prom<TA, TC>::T, typename Prom<TV, TM>::T>::T, TS>::T>& out) {
+  typedef typename Prom<TA, TC>::T TG;
+  GpGeom<TA> g;
+  gp_geom(a, g);
+  TG b[3], Gam[3][2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    b[k] = c[k][0] * g.n[0] + c[k][1] * g.n[1] + c[k][2] * g.n[2];
+#pragma unroll
+    for (int mu = 0; mu < 2; ++mu) Gam[k][mu] = c[k][0] * g.up[mu][0] + c[k][1] * g.up[mu][1] + c[k][2] * g.up[mu][2];
+  }
+  gp_core<MOTION>(g, a, b, Gam, dv, v, dm, vm, lam, pm, mat, out);
 }
 
 // ---- Neumann boundary Gauss point (FiniteElement.jl:363-384, calc_tau_nu :431-452) -------------------------
