@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmembrane_b200.so")
+LIB_PATH = os.environ.get("MAF_LIB", os.path.join(_HERE, "csrc", "libmembrane_b200.so"))
 
 PATTERN_BLK, PATTERN_SYM = 0, 1
 SCATTER_ATOMIC, SCATTER_DETERMINISTIC = 0, 1

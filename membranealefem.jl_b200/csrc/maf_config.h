@@ -78,20 +78,25 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   for (int f = 0; f < NFIELD; ++f) { rlo[f] = 99; rhi[f] = -1; }
   for (int f = 0; f < NFIELD; ++f)
     for (int g = 0; g < NFIELD; ++g) cfg.coloff[f][g] = -1;
+  auto is_mesh = [&](const B& b) { return b.nc == 5 && b.d0 == 1 && b.g == cfg.mesh_field; };
   for (const B& b : bl) {
     rlo[b.f] = std::min(rlo[b.f], b.c0);
     rhi[b.f] = std::max(rhi[b.f], b.c0 + b.nr);
     cfg.cd0[b.f][b.g] = b.d0;
-    cfg.cnc[b.f][b.g] = b.nc;
+    cfg.cnc[b.f][b.g] = is_mesh(b) ? 2 : b.nc;   // mesh blocks store N1,N2 per dof j and 3 shared b-direction columns
+    if (b.nc == 5 && !is_mesh(b)) throw std::runtime_error("a 5-channel block must be a mesh-column block");
   }
   int off = 0;
   for (int f = 0; f < NFIELD; ++f) {
-    if (rhi[f] < 0) { cfg.rc0[f] = 0; cfg.rnc[f] = 0; cfg.aoff[f] = off; cfg.ald[f] = 0; continue; }
+    if (rhi[f] < 0) { cfg.rc0[f] = 0; cfg.rnc[f] = 0; cfg.aoff[f] = off; cfg.ald[f] = 0; cfg.bcol[f] = -1; continue; }
     cfg.rc0[f] = rlo[f];
     cfg.rnc[f] = rhi[f] - rlo[f];
     int ld = 0;
+    cfg.bcol[f] = -1;
     for (int g = 0; g < NFIELD; ++g)
       if (cfg.cnc[f][g] > 0) { cfg.coloff[f][g] = ld; ld += cfg.ncomp[g] * cfg.cnc[f][g]; }
+    for (const B& b : bl)
+      if (b.f == f && is_mesh(b)) { cfg.bcol[f] = ld; ld += 3; }
     ld += ld & 1;
     cfg.ald[f] = ld;
     cfg.aoff[f] = off;
@@ -102,8 +107,9 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   cfg.nblocks = (int)bl.size();
   for (int k = 0; k < cfg.nblocks; ++k) {
     const B& b = bl[k];
+    const bool q = is_mesh(b) && (b.f == F_V || (b.f == F_M && motion == M_ALEVB));
     cfg.blocks[k] = Block{(int8_t)b.f, (int8_t)b.g, (int8_t)b.c0, (int8_t)b.nr, (int8_t)b.d0, (int8_t)b.nc,
-                          (int8_t)kind_of(b.nr, b.nc), (int8_t)b.db};
+                          (int8_t)kind_of(b.nr, b.nc), (int8_t)b.db, (int8_t)(is_mesh(b) ? 1 : 0), (int8_t)(q ? 1 : 0)};
   }
   // tangent tasks, heaviest kinds first so that the lanes of a warp share a code path
   std::vector<Task> tasks;
@@ -224,7 +230,11 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   cfg.o_phi = o; o += 486;
   cfg.o_E = o; o += 9 * E_STRIDE;
   cfg.o_S = o; o += 9 * S_STRIDE;
+  cfg.o_G = o; o += 9 * G_STRIDE;
   cfg.o_int = o; o += (I_END + 1) / 2;
+  o += o & 1;
+  cfg.o_scp = o; o += 72;
+  cfg.o_spo = o; o += 81;
   o += o & 1;
   cfg.o_A = o; o += 9 * cfg.asize;
   cfg.smem_doubles = o;

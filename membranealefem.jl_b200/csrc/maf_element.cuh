@@ -24,6 +24,8 @@ struct Block {      // one (row field, col field) tangent block type
   int8_t d0, nc;    // col channel range [d0, d0+nc)
   int8_t kind;      // dispatch id for the <NR,NC> instantiation
   int8_t db;        // add the Dohrmann-Bochev matrix (lambda-lambda and pm-pm blocks)
+  int8_t mesh;      // columns are the dofs that move the mesh, incl. the second-derivative channels N11,N22,N12
+  int8_t qterm;     // mesh block whose rows carry the moment term -Q_k Gamma^mu_k (v rows; vm rows for ALEVB)
 };
 struct Task {       // 27 outputs of one block: rows (a1 = 0..2, a2), all 9 column nodes b
   uint8_t blk, i, j, a2;
@@ -47,6 +49,9 @@ struct Config {
   int rc0[NFIELD], rnc[NFIELD];
   int cd0[NFIELD][NFIELD], cnc[NFIELD][NFIELD];
   int aoff[NFIELD], ald[NFIELD], coloff[NFIELD][NFIELD];
+  // second derivatives of x enter only through b_k = x_{,k}.n and Gamma: the three b-direction columns
+  // w dt dS/db_k are stored ONCE per row at bcol[f] (not per mesh dof j) and expanded inside the contraction
+  int bcol[NFIELD];
   int asize;                      // doubles per Gauss point
   int nblocks;
   Block blocks[MAF_MAX_BLOCKS];
@@ -63,7 +68,7 @@ struct Config {
   Material mat;
   double dbscale;                 // adb / zv
   // shared-memory layout (offsets in doubles from the element's block)
-  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_A, o_int, smem_doubles;
+  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_G, o_A, o_int, o_scp, o_spo, smem_doubles;
 };
 
 // interpolated Gauss-point inputs E[gp][.]
@@ -72,6 +77,8 @@ enum { E_A = 0, E_C = 6, E_DV = 15, E_V = 21, E_DM = 24, E_VM = 30, E_LAM = 33, 
 enum { S_V = 0, S_M = 18, S_L = 36, S_P = 37, S_STRIDE = 38 };
 // integer scratch (int32 view of the o_int region)
 enum { I_NODE = 0, I_EQ = 9, I_MASK = 81, I_PAIR = 90, I_END = 171 };
+// per Gauss point geometry for the b-direction expansion: n[3], a^1[3], a^2[3], then w dt Q_k[i] (k-major)
+enum { G_N = 0, G_UP = 3, G_QW = 9, G_STRIDE = 18 };
 
 // read-only device tables shared by all elements
 struct Tables {
@@ -134,6 +141,25 @@ MAF_HD void phase_gather(int tid, int nt, const Config& cfg, const Tables& T, in
       for (int b = 0; b < 9; ++b) si[I_PAIR + 9 * a + b] = T.elpair[81 * el + 9 * a + b];
     }
   }
+  // scatter maps of this element, looked up once: column pointers of (b, J) and the pairoff row of (a, b)
+  int64_t* scp = reinterpret_cast<int64_t*>(sm + cfg.o_scp);
+  unsigned long long* spo = reinterpret_cast<unsigned long long*>(sm + cfg.o_spo);
+  for (int k = tid; k < 72 + 81; k += nt) {
+    if (k < 72) {
+      const int b = k >> 3, J = k & 7;
+      int64_t cp = 0;
+      if (J < cfg.ndf) {
+        const int32_t eq = T.ID[(int64_t)cfg.ndf * T.IX[9 * el + b] + J];
+        if (eq >= 0) cp = T.colptr[eq];
+      }
+      scp[k] = cp;
+    } else {
+      const uint8_t* row = T.pairoff + (int64_t)T.elpair[81 * el + (k - 72)] * 8;
+      unsigned long long wv = 0;
+      for (int q = 7; q >= 0; --q) wv = (wv << 8) | row[q];
+      spo[k - 72] = wv;
+    }
+  }
   // basis table of this element: Phi[gp][c][a] = (1-D factor dir 1) * (1-D factor dir 2), one product each
   const int e1 = (int)(el % T.num1el), e2 = (int)(el / T.num1el);
   const double* l1 = T.line1 + 30 * T.uel1[e1];
@@ -177,6 +203,10 @@ MAF_HD int a_index(const Config& cfg, int f, int i, int c, int g, int j, int d) 
   return cfg.aoff[f] + (i * cfg.rnc[f] + (c - cfg.rc0[f])) * cfg.ald[f] + cfg.coloff[f][g] + j * cfg.cnc[f][g] +
          (d - cfg.cd0[f][g]);
 }
+// address of the b-direction column k of row (f, i, c)
+MAF_HD int b_index(const Config& cfg, int f, int i, int c, int k) {
+  return cfg.aoff[f] + (i * cfg.rnc[f] + (c - cfg.rc0[f])) * cfg.ald[f] + cfg.bcol[f] + k;
+}
 // does row field f keep a column for trial (g, ., d)?
 MAF_HD bool has_col(const Config& cfg, int f, int g, int d) {
   return cfg.coloff[f][g] >= 0 && d >= cfg.cd0[f][g] && d < cfg.cd0[f][g] + cfg.cnc[f][g];
@@ -211,6 +241,7 @@ MAF_HD void zero_column(const Config& cfg, double* Agp, int g, int j, int d) {
   for (int f = 0; f < 2; ++f) {
     if (!has_col(cfg, f, g, d)) continue;
     const int base = a_index(cfg, f, 0, cfg.rc0[f], g, j, d), ld = cfg.ald[f], nrow = 3 * cfg.rnc[f];
+#pragma unroll 1
     for (int r = 0; r < nrow; ++r) Agp[base + r * ld] = 0.0;
   }
   if (has_col(cfg, F_L, g, d)) Agp[a_index(cfg, F_L, 0, CH_N, g, j, d)] = 0.0;
@@ -297,52 +328,34 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, double
   }
 
   if (it.type == IT_GEO_B) {
-    const bool mrows = (MOTION == M_ALEVB);  // the mesh rows carry the bending moment only for ALEVB
+    const double wdt = w * dt;
+    double* Gg = sm + cfg.o_G + G_STRIDE * gp;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { Gg[G_N + i] = g.n[i]; Gg[G_UP + i] = g.up[0][i]; Gg[G_UP + 3 + i] = g.up[1][i]; }
+#pragma unroll 1
     for (int k = 0; k < 3; ++k) {
       Dual bd[3] = {Dual(b[0], k == 0 ? 1.0 : 0.0), Dual(b[1], k == 1 ? 1.0 : 0.0), Dual(b[2], k == 2 ? 1.0 : 0.0)};
       GpStress<Dual> S;
       gp_core<MOTION>(g, a, bd, Gam, dv, v, dm, vm, lam, pm, cfg.mat, S);
-      // Q_k[i] = J M~^k n_i is the primal N_k row of the velocity equations
-      double Qk[3];
+      // Q_k[i] = J M~^k n_i (the primal N_k row of the velocity equations) for the Gamma term
 #pragma unroll
       for (int i = 0; i < 3; ++i)
-        Qk[i] = k == 0 ? S.Sv[CH_N11][i].v : (k == 1 ? S.Sv[CH_N22][i].v : S.Sv[CH_N12][i].v);
-      const double wdt = w * dt;
+        Gg[G_QW + 3 * k + i] = wdt * (k == 0 ? S.Sv[CH_N11][i].v : (k == 1 ? S.Sv[CH_N22][i].v : S.Sv[CH_N12][i].v));
+      if (cfg.bcol[F_V] >= 0) {
+        const int base = b_index(cfg, F_V, 0, cfg.rc0[F_V], k), ld = cfg.ald[F_V], nr = cfg.rnc[F_V], c0 = cfg.rc0[F_V];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int d = CH_N11 + k;
-        const double nj = g.n[j], u0 = g.up[0][j], u1 = g.up[1][j];
-        if (has_col(cfg, F_V, mf, d)) {
-          const int base = a_index(cfg, F_V, 0, cfg.rc0[F_V], mf, j, d), ld = cfg.ald[F_V], nr = cfg.rnc[F_V],
-                    c0 = cfg.rc0[F_V];
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
+          for (int cc = 0; cc < NCH; ++cc)
+            if (cc >= c0 && cc < c0 + nr) Agp[base + (i * nr + (cc - c0)) * ld] = wdt * S.Sv[cc][i].d;
+      }
+      if (cfg.bcol[F_M] >= 0) {
+        const int base = b_index(cfg, F_M, 0, cfg.rc0[F_M], k), ld = cfg.ald[F_M], nr = cfg.rnc[F_M], c0 = cfg.rc0[F_M];
 #pragma unroll
-            for (int cc = 0; cc < NCH; ++cc) {
-              if (cc < c0 || cc >= c0 + nr) continue;
-              double val = S.Sv[cc][i].d * nj;
-              if (cc == CH_N1) val -= Qk[i] * u0;
-              if (cc == CH_N2) val -= Qk[i] * u1;
-              Agp[base + (i * nr + (cc - c0)) * ld] = wdt * val;
-            }
-        }
-        if (has_col(cfg, F_M, mf, d)) {
-          const int base = a_index(cfg, F_M, 0, cfg.rc0[F_M], mf, j, d), ld = cfg.ald[F_M], nr = cfg.rnc[F_M],
-                    c0 = cfg.rc0[F_M];
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int cc = 0; cc < NCH; ++cc) {
-              if (cc < c0 || cc >= c0 + nr) continue;
-              double val = S.Sm[cc][i].d * nj;
-              if (mrows && cc == CH_N1) val -= Qk[i] * u0;
-              if (mrows && cc == CH_N2) val -= Qk[i] * u1;
-              Agp[base + (i * nr + (cc - c0)) * ld] = wdt * val;
-            }
-        }
-        // the lambda and pm rows do not depend on the second derivatives of x
-        if (has_col(cfg, F_L, mf, d)) Agp[a_index(cfg, F_L, 0, CH_N, mf, j, d)] = 0.0;
-        if (has_col(cfg, F_P, mf, d)) Agp[a_index(cfg, F_P, 0, CH_N, mf, j, d)] = 0.0;
+          for (int cc = 0; cc < NCH; ++cc)
+            if (cc >= c0 && cc < c0 + nr) Agp[base + (i * nr + (cc - c0)) * ld] = wdt * S.Sm[cc][i].d;
       }
     }
     return;
@@ -504,6 +517,66 @@ MAF_HD void block_accumulate(const double* __restrict__ A0, int asize, int ald, 
   }
 }
 
+// Mesh-column block: trial channels N1,N2 (per mesh dof j, stored) and N11,N22,N12 (expanded on the fly from the
+// b-direction columns):  A[(i,c)][(j,N_k)] = n_j * Ab_k[(i,c)] - [c = N_mu] a^mu_j * (w dt Q_k[i]).
+template <int NR>
+MAF_HD void block_accumulate_mesh(const double* __restrict__ A0, int asize, int ald, int boff,
+                                  const double* __restrict__ Phi, const double* __restrict__ G, int c0, int a2, int i,
+                                  int j, bool qterm, double acc[3][9]) {
+#pragma unroll
+  for (int a1 = 0; a1 < 3; ++a1)
+#pragma unroll
+    for (int b = 0; b < 9; ++b) acc[a1][b] = 0.0;
+  for (int gp = 0; gp < 9; ++gp) {
+    const double* Ag = A0 + (size_t)asize * gp;
+    const double* Pg = Phi + 54 * gp;
+    const double* Gg = G + G_STRIDE * gp;
+    double u[3][5];
+#pragma unroll
+    for (int a1 = 0; a1 < 3; ++a1)
+#pragma unroll
+      for (int d = 0; d < 5; ++d) u[a1][d] = 0.0;
+#pragma unroll
+    for (int c = 0; c < NR; ++c) {
+      const double p0 = Pg[9 * (c0 + c) + 3 * a2], p1 = Pg[9 * (c0 + c) + 3 * a2 + 1], p2 = Pg[9 * (c0 + c) + 3 * a2 + 2];
+      const double* row = Ag + c * ald;
+#pragma unroll
+      for (int d = 0; d < 5; ++d) {
+        const double av = d < 2 ? row[d] : row[boff + d - 2];
+        u[0][d] += p0 * av;
+        u[1][d] += p1 * av;
+        u[2][d] += p2 * av;
+      }
+    }
+    const double nj = Gg[G_N + j];
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    if (qterm) {
+      const double u0 = Gg[G_UP + j], u1 = Gg[G_UP + 3 + j];
+      const double* P1 = Pg + 9 * CH_N1 + 3 * a2;
+      const double* P2 = Pg + 9 * CH_N2 + 3 * a2;
+      t0 = u0 * P1[0] + u1 * P2[0];
+      t1 = u0 * P1[1] + u1 * P2[1];
+      t2 = u0 * P1[2] + u1 * P2[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double qw = qterm ? Gg[G_QW + 3 * k + i] : 0.0;
+      u[0][2 + k] = nj * u[0][2 + k] - qw * t0;
+      u[1][2 + k] = nj * u[1][2 + k] - qw * t1;
+      u[2][2 + k] = nj * u[2][2 + k] - qw * t2;
+    }
+#pragma unroll
+    for (int d = 0; d < 5; ++d)
+#pragma unroll
+      for (int b = 0; b < 9; ++b) {
+        const double pb = Pg[9 * (CH_N1 + d) + b];
+        acc[0][b] += u[0][d] * pb;
+        acc[1][b] += u[1][d] * pb;
+        acc[2][b] += u[2][d] * pb;
+      }
+  }
+}
+
 // destination of the 27 outputs of a task
 struct KSink {
   double* nzval;            // atomics path: global CSC values
@@ -520,6 +593,9 @@ MAF_HD void phase_tangent_task(const Config& cfg, const Tables& T, int64_t el, i
   const double* A0 = sm + cfg.o_A + a_index(cfg, f, i, bk.c0, g, j, bk.d0);
   const double* Phi = sm + cfg.o_phi;
   const int ald = cfg.ald[f];
+  // offset from the (j, N1) entry of a row to its b-direction columns
+  const int boff = bk.mesh ? cfg.bcol[f] - (cfg.coloff[f][g] + j * cfg.cnc[f][g]) : 0;
+  const double* G = sm + cfg.o_G;
   double acc[3][9];
   switch (bk.kind) {
     case 0: block_accumulate<1, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
@@ -527,9 +603,9 @@ MAF_HD void phase_tangent_task(const Config& cfg, const Tables& T, int64_t el, i
     case 2: block_accumulate<1, 3>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
     case 3: block_accumulate<2, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
     case 4: block_accumulate<2, 2>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
-    case 5: block_accumulate<3, 5>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
-    case 6: block_accumulate<5, 5>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
-    default: block_accumulate<6, 5>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
+    case 5: block_accumulate_mesh<3>(A0, cfg.asize, ald, boff, Phi, G, bk.c0, a2, i, j, bk.qterm, acc); break;
+    case 6: block_accumulate_mesh<5>(A0, cfg.asize, ald, boff, Phi, G, bk.c0, a2, i, j, bk.qterm, acc); break;
+    default: block_accumulate_mesh<6>(A0, cfg.asize, ald, boff, Phi, G, bk.c0, a2, i, j, bk.qterm, acc); break;
   }
   const int32_t* si = reinterpret_cast<const int32_t*>(sm + cfg.o_int);
   if (bk.db) {  // Dohrmann-Bochev stabilisation matrix (state independent), FiniteElement.jl:323-327
@@ -550,18 +626,25 @@ MAF_HD void phase_tangent_task(const Config& cfg, const Tables& T, int64_t el, i
   }
   // atomics path: K_gl[LM[i], LM[j]] += K_el[i, j] for active rows and columns (FiniteElement.jl:129-136)
   const int I = cfg.fdof[f][i], J = cfg.fdof[g][j];
-  const unsigned rmask = cfg.rowmask[J];
+  const unsigned rmask = cfg.rowmask[J] & ((1u << I) - 1u);
+  const int64_t* scp = reinterpret_cast<const int64_t*>(sm + cfg.o_scp);
+  const unsigned long long* spo = reinterpret_cast<const unsigned long long*>(sm + cfg.o_spo);
+  int rank[3];
+  bool act[3];
+#pragma unroll
+  for (int a1 = 0; a1 < 3; ++a1) {
+    const unsigned m = (unsigned)si[I_MASK + a1 + 3 * a2];
+    act[a1] = (m >> I) & 1u;
+    rank[a1] = popc8(m & rmask);
+  }
 #pragma unroll
   for (int b = 0; b < 9; ++b) {
-    const int eqc = si[I_EQ + 8 * b + J];
-    if (eqc < 0) continue;  // columns exist only for active dofs (FiniteElement.jl:111)
-    const int64_t cp = T.colptr[eqc];
+    if (si[I_EQ + 8 * b + J] < 0) continue;  // columns exist only for active dofs (FiniteElement.jl:111)
+    const int64_t cp = scp[8 * b + J];
 #pragma unroll
     for (int a1 = 0; a1 < 3; ++a1) {
-      const int a = a1 + 3 * a2;
-      const unsigned m = (unsigned)si[I_MASK + a];
-      if (!((m >> I) & 1u)) continue;
-      const int64_t slot = cp + T.pairoff[(int64_t)si[I_PAIR + 9 * a + b] * 8 + J] + popc8(m & rmask & ((1u << I) - 1u));
+      if (!act[a1]) continue;
+      const int64_t slot = cp + (int64_t)((spo[9 * (a1 + 3 * a2) + b] >> (8 * J)) & 255ull) + rank[a1];
       atomic_add(&sink.nzval[slot], acc[a1][b]);
     }
   }
