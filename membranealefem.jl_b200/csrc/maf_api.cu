@@ -409,6 +409,7 @@ int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* pa
     h->T.colptr = upload(h, M.sym.colptr.data(), M.sym.colptr.size());
     h->T.elpair = upload(h, M.sym.elpair.data(), M.sym.elpair.size());
     h->T.pairoff = upload(h, M.sym.pairoff.data(), M.sym.pairoff.size());
+    h->T.eq0 = upload(h, M.sym.eq0.data(), M.sym.eq0.size());
     h->T.numnp = M.numnp; h->T.numel = M.numel; h->T.num1el = M.num1el; h->T.nuel1 = M.nuel1;
     h->BT.edge1 = upload(h, M.edge1.data(), M.edge1.size());
     h->BT.edge2 = upload(h, M.edge2.data(), M.edge2.size());

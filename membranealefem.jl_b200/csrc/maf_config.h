@@ -96,7 +96,7 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
     for (int g = 0; g < NFIELD; ++g)
       if (cfg.cnc[f][g] > 0) { cfg.coloff[f][g] = ld; ld += cfg.ncomp[g] * cfg.cnc[f][g]; }
     for (const B& b : bl)
-      if (b.f == f && is_mesh(b)) { cfg.bcol[f] = ld; ld += 3; }
+      if (b.f == f && is_mesh(b)) { ld += ld & 1; cfg.bcol[f] = ld; ld += 3; }   // 16-byte aligned for LDS.128
     ld += ld & 1;
     cfg.ald[f] = ld;
     cfg.aoff[f] = off;
@@ -227,17 +227,25 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   cfg.o_cl = o; o += 9;
   cfg.o_cp = o; o += 9;
   cfg.o_w = o; o += 9;
-  cfg.o_phi = o; o += 486;
+  cfg.o_phi = o; o += PHI_DOUBLES;
+  cfg.o_FG = o; o += 9 * FG_STRIDE;
   cfg.o_E = o; o += 9 * E_STRIDE;
   cfg.o_S = o; o += 9 * S_STRIDE;
   cfg.o_G = o; o += 9 * G_STRIDE;
   cfg.o_int = o; o += (I_END + 1) / 2;
   o += o & 1;
-  cfg.o_scp = o; o += 72;
-  cfg.o_spo = o; o += 81;
-  o += o & 1;
+  cfg.o_slot = o; o += 81 * 8 / 2;
+  cfg.o_base = o; o += 2;
   cfg.o_A = o; o += 9 * cfg.asize;
   cfg.smem_doubles = o;
+  // everything that is read with 16-byte loads must sit on an even double offset
+  bool ok = !(cfg.o_A & 1) && !(cfg.o_phi & 1) && !(cfg.o_FG & 1) && !(cfg.asize & 1) && !(cfg.o_base & 1);
+  for (int f = 0; f < NFIELD; ++f) {
+    ok = ok && !(cfg.aoff[f] & 1) && !(cfg.ald[f] & 1) && (cfg.bcol[f] < 0 || !(cfg.bcol[f] & 1));
+    for (int g = 0; g < NFIELD; ++g)
+      if (cfg.bcol[f] >= 0 && g == cfg.mesh_field && cfg.coloff[f][g] >= 0) ok = ok && !(cfg.coloff[f][g] & 1);
+  }
+  if (!ok) throw std::runtime_error("internal: misaligned shared-memory layout");
 }
 
 // Dohrmann-Bochev matrices tmpDB = G^T H^-1 G of every unique element (FiniteElement.jl:279-281, 315-323):

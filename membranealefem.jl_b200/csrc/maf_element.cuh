@@ -68,7 +68,7 @@ struct Config {
   Material mat;
   double dbscale;                 // adb / zv
   // shared-memory layout (offsets in doubles from the element's block)
-  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_G, o_A, o_int, o_scp, o_spo, smem_doubles;
+  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_G, o_A, o_int, o_slot, o_base, o_FG, smem_doubles;
 };
 
 // interpolated Gauss-point inputs E[gp][.]
@@ -93,9 +93,18 @@ struct Tables {
   const int64_t* colptr;    // nmdf+1, 0-based
   const int32_t* elpair;    // numel x 81: index of (A = node a, B = node b) in the node-adjacency list of B
   const uint8_t* pairoff;   // npairs x 8: rows that precede node A's rows in column (B,J)
+  const int32_t* eq0;       // numnp: an equation number whose column pointer bounds the node's columns from below
   int64_t numnp, numel;
   int num1el, nuel1;
 };
+
+// shared-memory basis table: Phi[gp][c][a2][4] (node a = a1 + 3 a2 at 4 a2 + a1; the pad keeps the three values
+// of a node row 16-byte aligned so that they load as LDS.128 + LDS.64)
+enum { PHI_C = 12, PHI_GP = 72, PHI_DOUBLES = 9 * 72, FG_STRIDE = 18 };
+#define SLOT_NONE (-2147483647 - 1)
+MAF_HD int phi_a(int a) { return 4 * (a / 3) + (a % 3); }
+struct alignas(16) dbl2 { double x, y; };
+MAF_HD dbl2 ld2(const double* p) { return *reinterpret_cast<const dbl2*>(p); }
 
 #if defined(__CUDA_ARCH__)
 MAF_HD void atomic_add(double* p, double v) { atomicAdd(p, v); }
@@ -141,38 +150,47 @@ MAF_HD void phase_gather(int tid, int nt, const Config& cfg, const Tables& T, in
       for (int b = 0; b < 9; ++b) si[I_PAIR + 9 * a + b] = T.elpair[81 * el + 9 * a + b];
     }
   }
-  // scatter maps of this element, looked up once: column pointers of (b, J) and the pairoff row of (a, b)
-  int64_t* scp = reinterpret_cast<int64_t*>(sm + cfg.o_scp);
-  unsigned long long* spo = reinterpret_cast<unsigned long long*>(sm + cfg.o_spo);
-  for (int k = tid; k < 72 + 81; k += nt) {
-    if (k < 72) {
-      const int b = k >> 3, J = k & 7;
-      int64_t cp = 0;
-      if (J < cfg.ndf) {
-        const int32_t eq = T.ID[(int64_t)cfg.ndf * T.IX[9 * el + b] + J];
-        if (eq >= 0) cp = T.colptr[eq];
-      }
-      scp[k] = cp;
-    } else {
-      const uint8_t* row = T.pairoff + (int64_t)T.elpair[81 * el + (k - 72)] * 8;
-      unsigned long long wv = 0;
-      for (int q = 7; q >= 0; --q) wv = (wv << 8) | row[q];
-      spo[k - 72] = wv;
+  // scatter map of this element, looked up once: slot of (first row of node a, column (b, J)) relative to the
+  // first column pointer of the element's first node  ->  sslot[(9 a + b) * 8 + J]   (int32)
+  int32_t* sslot = reinterpret_cast<int32_t*>(sm + cfg.o_slot);
+  const int64_t base = T.colptr[T.eq0[T.IX[9 * el]]];
+  for (int k = tid; k < 81 * 8; k += nt) {
+    const int J = k & 7, ab = k >> 3, b = ab % 9;
+    int32_t rel = SLOT_NONE;   // columns exist only for active dofs (FiniteElement.jl:111)
+    if (J < cfg.ndf) {
+      const int32_t eq = T.ID[(int64_t)cfg.ndf * T.IX[9 * el + b] + J];
+      if (eq >= 0) rel = (int32_t)(T.colptr[eq] - base) + (int32_t)T.pairoff[(int64_t)T.elpair[81 * el + ab] * 8 + J];
     }
+    sslot[k] = rel;
   }
+  if (tid == 0) *reinterpret_cast<int64_t*>(sm + cfg.o_base) = base;
   // basis table of this element: Phi[gp][c][a] = (1-D factor dir 1) * (1-D factor dir 2), one product each
   const int e1 = (int)(el % T.num1el), e2 = (int)(el / T.num1el);
   const double* l1 = T.line1 + 30 * T.uel1[e1];
   const double* l2 = T.line2 + 30 * T.uel2[e2];
-  for (int k = tid; k < 9 * 54; k += nt) {
-    const int a = k % 9, c = (k / 9) % 6, gp = k / 54;
-    const int g1 = gp % 3, g2 = gp / 3, a1 = a % 3, a2 = a / 3;
+  for (int k = tid; k < 54 * 3; k += nt) {   // one (gp, channel, node row a2) per thread: three products
+    const int a2 = k % 3, c = (k / 3) % 6, gp = k / 18;
+    const int g1 = gp % 3, g2 = gp / 3;
     // derivative orders per channel: N(0,0) N1(1,0) N2(0,1) N11(2,0) N22(0,2) N12(1,1)
     const int o1 = (c == CH_N1 || c == CH_N12) ? 1 : (c == CH_N11 ? 2 : 0);
     const int o2 = (c == CH_N2 || c == CH_N12) ? 1 : (c == CH_N22 ? 2 : 0);
-    sm[cfg.o_phi + k] = l1[10 * g1 + 1 + 3 * o1 + a1] * l2[10 * g2 + 1 + 3 * o2 + a2];
+    const double* f = l1 + 10 * g1 + 1 + 3 * o1;
+    const double gv = l2[10 * g2 + 1 + 3 * o2 + a2];
+    double* dst = sm + cfg.o_phi + PHI_GP * gp + PHI_C * c + 4 * a2;
+    dst[0] = f[0] * gv; dst[1] = f[1] * gv; dst[2] = f[2] * gv; dst[3] = 0.0;
+  }
+  // 1-D factors per Gauss point for the sum-factorised second contraction: f[order][b1] (9), g[order][b2] (9)
+  for (int k = tid; k < 9 * FG_STRIDE; k += nt) {
+    const int gp = k / FG_STRIDE, q = k % FG_STRIDE;
+    sm[cfg.o_FG + k] = q < 9 ? l1[10 * (gp % 3) + 1 + q] : l2[10 * (gp / 3) + 1 + (q - 9)];
   }
   for (int gp = tid; gp < 9; gp += nt) sm[cfg.o_w + gp] = l1[10 * (gp % 3)] * l2[10 * (gp / 3)];
+  // the closed-form columns of the Gauss-point tangent touch only a few rows: start from zero
+  {
+    dbl2* Az = reinterpret_cast<dbl2*>(sm + cfg.o_A);
+    const dbl2 z = {0.0, 0.0};
+    for (int k = tid; k < 9 * cfg.asize / 2; k += nt) Az[k] = z;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -190,10 +208,10 @@ MAF_HD void phase_interp(int tid, int nt, const Config& cfg, double* sm) {
     else if (q < 33) { ch = CH_N; src = cfg.o_cm + 9 * (q - 30); }
     else if (q == 33) { ch = CH_N; src = cfg.o_cl; }
     else { ch = CH_N; src = cfg.o_cp; }
-    const double* ph = sm + cfg.o_phi + 54 * gp + 9 * ch;
+    const double* ph = sm + cfg.o_phi + PHI_GP * gp + PHI_C * ch;
     double s = 0.0;
 #pragma unroll
-    for (int a = 0; a < 9; ++a) s += sm[src + a] * ph[a];
+    for (int a = 0; a < 9; ++a) s += sm[src + a] * ph[4 * (a / 3) + (a % 3)];
     sm[cfg.o_E + E_STRIDE * gp + q] = s;
   }
 }
@@ -382,7 +400,6 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, double
 #pragma unroll
       for (int mu = 0; mu < 2; ++mu) {
         const int d = CH_N1 + mu;
-        zero_column(cfg, Agp, F_V, j, d);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const double Pij = (i == j ? 1.0 : 0.0) - g.n[i] * g.n[j];
@@ -393,7 +410,6 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, double
         if (has_col(cfg, F_L, F_V, d)) Agp[a_index(cfg, F_L, 0, CH_N, F_V, j, d)] = wJ * g.up[mu][j];
       }
       if (MOTION == M_EUL || ALE) {  // (v, j, N): EUL d Sm[N][i] = -am J n_i n_j ; ALE d Sp = +J n_j
-        zero_column(cfg, Agp, F_V, j, CH_N);
         if (MOTION == M_EUL) {
 #pragma unroll
           for (int i = 0; i < 3; ++i) put(cfg, Agp, F_M, i, CH_N, F_V, j, CH_N, -wJ * am * g.n[i] * g.n[j]);
@@ -402,13 +418,11 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, double
       }
     }
     if (MOTION == M_EUL || ALE) {    // (vm, j, N): EUL d Sm[N][i] = am J delta_ij ; ALE d Sp = -J n_j
-      zero_column(cfg, Agp, F_M, j, CH_N);
       if (MOTION == M_EUL) put(cfg, Agp, F_M, j, CH_N, F_M, j, CH_N, wJ * am);
       if (ALE && has_col(cfg, F_P, F_M, CH_N)) Agp[a_index(cfg, F_P, 0, CH_N, F_M, j, CH_N)] = -wJ * g.n[j];
     }
   }
   {  // (lambda, N): d Sv[N_al][i] = J a^al_i ; d Sl = -adb/zv
-    zero_column(cfg, Agp, F_L, 0, CH_N);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -416,7 +430,6 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, double
     if (has_col(cfg, F_L, F_L, CH_N)) Agp[a_index(cfg, F_L, 0, CH_N, F_L, 0, CH_N)] = -w * kdb;
   }
   if (ALE) {  // (pm, N): d Sm[N][i] = -J n_i ; d Sp = -adb/zv
-    zero_column(cfg, Agp, F_P, 0, CH_N);
 #pragma unroll
     for (int i = 0; i < 3; ++i) put(cfg, Agp, F_M, i, CH_N, F_P, 0, CH_N, -wJ * g.n[i]);
     if (has_col(cfg, F_P, F_P, CH_N)) Agp[a_index(cfg, F_P, 0, CH_N, F_P, 0, CH_N)] = -w * kdb;
@@ -452,15 +465,15 @@ MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const Tables& T, 
     double s = 0.0;
     for (int gp = 0; gp < 9; ++gp) {
       const double* Sg = sm + cfg.o_S + S_STRIDE * gp;
-      const double* ph = sm + cfg.o_phi + 54 * gp;
+      const double* ph = sm + cfg.o_phi + PHI_GP * gp + phi_a(a);
       double t;
       if (f == F_V || f == F_M) {
         const int sb = f == F_V ? S_V : S_M;
         t = 0.0;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) t += Sg[sb + 3 * c + i] * ph[9 * c + a];
+        for (int c = 0; c < NCH; ++c) t += Sg[sb + 3 * c + i] * ph[PHI_C * c];
       } else {
-        t = Sg[f == F_L ? S_L : S_P] * ph[a];
+        t = Sg[f == F_L ? S_L : S_P] * ph[0];
       }
       s += sm[cfg.o_w + gp] * t;
     }
@@ -488,7 +501,7 @@ MAF_HD void block_accumulate(const double* __restrict__ A0, int asize, int ald, 
     for (int b = 0; b < 9; ++b) acc[a1][b] = 0.0;
   for (int gp = 0; gp < 9; ++gp) {
     const double* Ag = A0 + (size_t)asize * gp;
-    const double* Pg = Phi + 54 * gp;
+    const double* Pg = Phi + PHI_GP * gp;
     double u[3][NC];
 #pragma unroll
     for (int a1 = 0; a1 < 3; ++a1)
@@ -496,40 +509,48 @@ MAF_HD void block_accumulate(const double* __restrict__ A0, int asize, int ald, 
       for (int d = 0; d < NC; ++d) u[a1][d] = 0.0;
 #pragma unroll
     for (int c = 0; c < NR; ++c) {
-      const double p0 = Pg[9 * (c0 + c) + 3 * a2], p1 = Pg[9 * (c0 + c) + 3 * a2 + 1], p2 = Pg[9 * (c0 + c) + 3 * a2 + 2];
+      const dbl2 p01 = ld2(Pg + PHI_C * (c0 + c) + 4 * a2);
+      const double p2 = Pg[PHI_C * (c0 + c) + 4 * a2 + 2];
 #pragma unroll
       for (int d = 0; d < NC; ++d) {
         const double av = Ag[c * ald + d];
-        u[0][d] += p0 * av;
-        u[1][d] += p1 * av;
+        u[0][d] += p01.x * av;
+        u[1][d] += p01.y * av;
         u[2][d] += p2 * av;
       }
     }
 #pragma unroll
     for (int d = 0; d < NC; ++d)
 #pragma unroll
-      for (int b = 0; b < 9; ++b) {
-        const double pb = Pg[9 * (d0 + d) + b];
-        acc[0][b] += u[0][d] * pb;
-        acc[1][b] += u[1][d] * pb;
-        acc[2][b] += u[2][d] * pb;
+      for (int b2 = 0; b2 < 3; ++b2) {
+        const dbl2 q01 = ld2(Pg + PHI_C * (d0 + d) + 4 * b2);
+        const double q2 = Pg[PHI_C * (d0 + d) + 4 * b2 + 2];
+#pragma unroll
+        for (int a1 = 0; a1 < 3; ++a1) {
+          acc[a1][3 * b2] += u[a1][d] * q01.x;
+          acc[a1][3 * b2 + 1] += u[a1][d] * q01.y;
+          acc[a1][3 * b2 + 2] += u[a1][d] * q2;
+        }
       }
   }
 }
 
 // Mesh-column block: trial channels N1,N2 (per mesh dof j, stored) and N11,N22,N12 (expanded on the fly from the
 // b-direction columns):  A[(i,c)][(j,N_k)] = n_j * Ab_k[(i,c)] - [c = N_mu] a^mu_j * (w dt Q_k[i]).
+// The second contraction is sum-factorised over the tensor-product structure of the basis
+// (Phi^d_b = f^{d1}_{b1} g^{d2}_{b2}):  sum_d u_d Phi^d_b = f1 (u_N1 g0 + u_N12 g1) + f0 (u_N2 g1 + u_N22 g2) + f2 u_N11 g0.
 template <int NR>
 MAF_HD void block_accumulate_mesh(const double* __restrict__ A0, int asize, int ald, int boff,
-                                  const double* __restrict__ Phi, const double* __restrict__ G, int c0, int a2, int i,
-                                  int j, bool qterm, double acc[3][9]) {
+                                  const double* __restrict__ Phi, const double* __restrict__ FG,
+                                  const double* __restrict__ G, int c0, int a2, int i, int j, bool qterm,
+                                  double acc[3][9]) {
 #pragma unroll
   for (int a1 = 0; a1 < 3; ++a1)
 #pragma unroll
     for (int b = 0; b < 9; ++b) acc[a1][b] = 0.0;
   for (int gp = 0; gp < 9; ++gp) {
     const double* Ag = A0 + (size_t)asize * gp;
-    const double* Pg = Phi + 54 * gp;
+    const double* Pg = Phi + PHI_GP * gp;
     const double* Gg = G + G_STRIDE * gp;
     double u[3][5];
 #pragma unroll
@@ -538,41 +559,56 @@ MAF_HD void block_accumulate_mesh(const double* __restrict__ A0, int asize, int 
       for (int d = 0; d < 5; ++d) u[a1][d] = 0.0;
 #pragma unroll
     for (int c = 0; c < NR; ++c) {
-      const double p0 = Pg[9 * (c0 + c) + 3 * a2], p1 = Pg[9 * (c0 + c) + 3 * a2 + 1], p2 = Pg[9 * (c0 + c) + 3 * a2 + 2];
+      const dbl2 p01 = ld2(Pg + PHI_C * (c0 + c) + 4 * a2);
+      const double p2 = Pg[PHI_C * (c0 + c) + 4 * a2 + 2];
       const double* row = Ag + c * ald;
+      const dbl2 a01 = ld2(row);          // (j, N1), (j, N2)
+      const dbl2 b01 = ld2(row + boff);   // b-directions 11, 22
+      const double b2v = row[boff + 2];   // b-direction 12
+      const double av[5] = {a01.x, a01.y, b01.x, b01.y, b2v};
 #pragma unroll
       for (int d = 0; d < 5; ++d) {
-        const double av = d < 2 ? row[d] : row[boff + d - 2];
-        u[0][d] += p0 * av;
-        u[1][d] += p1 * av;
-        u[2][d] += p2 * av;
+        u[0][d] += p01.x * av[d];
+        u[1][d] += p01.y * av[d];
+        u[2][d] += p2 * av[d];
       }
     }
     const double nj = Gg[G_N + j];
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    double t[3] = {0.0, 0.0, 0.0};
     if (qterm) {
       const double u0 = Gg[G_UP + j], u1 = Gg[G_UP + 3 + j];
-      const double* P1 = Pg + 9 * CH_N1 + 3 * a2;
-      const double* P2 = Pg + 9 * CH_N2 + 3 * a2;
-      t0 = u0 * P1[0] + u1 * P2[0];
-      t1 = u0 * P1[1] + u1 * P2[1];
-      t2 = u0 * P1[2] + u1 * P2[2];
+      const dbl2 P1 = ld2(Pg + PHI_C * CH_N1 + 4 * a2), P2 = ld2(Pg + PHI_C * CH_N2 + 4 * a2);
+      t[0] = u0 * P1.x + u1 * P2.x;
+      t[1] = u0 * P1.y + u1 * P2.y;
+      t[2] = u0 * Pg[PHI_C * CH_N1 + 4 * a2 + 2] + u1 * Pg[PHI_C * CH_N2 + 4 * a2 + 2];
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const double qw = qterm ? Gg[G_QW + 3 * k + i] : 0.0;
-      u[0][2 + k] = nj * u[0][2 + k] - qw * t0;
-      u[1][2 + k] = nj * u[1][2 + k] - qw * t1;
-      u[2][2 + k] = nj * u[2][2 + k] - qw * t2;
+#pragma unroll
+      for (int a1 = 0; a1 < 3; ++a1) u[a1][2 + k] = nj * u[a1][2 + k] - qw * t[a1];
     }
+    // f[order][b1] at Fg[3*order + b1], g[order][b2] at Fg[9 + 3*order + b2]
+    const double* Fg = FG + FG_STRIDE * gp;
+    double fg[18];
 #pragma unroll
-    for (int d = 0; d < 5; ++d)
+    for (int q = 0; q < 9; ++q) { const dbl2 v2 = ld2(Fg + 2 * q); fg[2 * q] = v2.x; fg[2 * q + 1] = v2.y; }
 #pragma unroll
-      for (int b = 0; b < 9; ++b) {
-        const double pb = Pg[9 * (CH_N1 + d) + b];
-        acc[0][b] += u[0][d] * pb;
-        acc[1][b] += u[1][d] * pb;
-        acc[2][b] += u[2][d] * pb;
+    for (int a1 = 0; a1 < 3; ++a1)
+#pragma unroll
+      for (int b2 = 0; b2 < 3; ++b2) {
+        const double g0 = fg[9 + b2], g1 = fg[12 + b2], g2 = fg[15 + b2];
+        const double t1 = u[a1][0] * g0 + u[a1][4] * g1;   // multiplies f1[b1]   (N1, N12)
+        const double t0 = u[a1][1] * g1 + u[a1][3] * g2;   // multiplies f0[b1]   (N2, N22)
+        const double t2 = u[a1][2] * g0;                   // multiplies f2[b1]   (N11)
+#pragma unroll
+        for (int b1 = 0; b1 < 3; ++b1) {   // three separate multiply-adds (each contracts to one DFMA)
+          double s = acc[a1][b1 + 3 * b2];
+          s += fg[3 + b1] * t1;
+          s += fg[b1] * t0;
+          s += fg[6 + b1] * t2;
+          acc[a1][b1 + 3 * b2] = s;
+        }
       }
   }
 }
@@ -596,6 +632,7 @@ MAF_HD void phase_tangent_task(const Config& cfg, const Tables& T, int64_t el, i
   // offset from the (j, N1) entry of a row to its b-direction columns
   const int boff = bk.mesh ? cfg.bcol[f] - (cfg.coloff[f][g] + j * cfg.cnc[f][g]) : 0;
   const double* G = sm + cfg.o_G;
+  const double* FG = sm + cfg.o_FG;
   double acc[3][9];
   switch (bk.kind) {
     case 0: block_accumulate<1, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
@@ -603,9 +640,9 @@ MAF_HD void phase_tangent_task(const Config& cfg, const Tables& T, int64_t el, i
     case 2: block_accumulate<1, 3>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
     case 3: block_accumulate<2, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
     case 4: block_accumulate<2, 2>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
-    case 5: block_accumulate_mesh<3>(A0, cfg.asize, ald, boff, Phi, G, bk.c0, a2, i, j, bk.qterm, acc); break;
-    case 6: block_accumulate_mesh<5>(A0, cfg.asize, ald, boff, Phi, G, bk.c0, a2, i, j, bk.qterm, acc); break;
-    default: block_accumulate_mesh<6>(A0, cfg.asize, ald, boff, Phi, G, bk.c0, a2, i, j, bk.qterm, acc); break;
+    case 5: block_accumulate_mesh<3>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a2, i, j, bk.qterm, acc); break;
+    case 6: block_accumulate_mesh<5>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a2, i, j, bk.qterm, acc); break;
+    default: block_accumulate_mesh<6>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a2, i, j, bk.qterm, acc); break;
   }
   const int32_t* si = reinterpret_cast<const int32_t*>(sm + cfg.o_int);
   if (bk.db) {  // Dohrmann-Bochev stabilisation matrix (state independent), FiniteElement.jl:323-327
@@ -627,25 +664,18 @@ MAF_HD void phase_tangent_task(const Config& cfg, const Tables& T, int64_t el, i
   // atomics path: K_gl[LM[i], LM[j]] += K_el[i, j] for active rows and columns (FiniteElement.jl:129-136)
   const int I = cfg.fdof[f][i], J = cfg.fdof[g][j];
   const unsigned rmask = cfg.rowmask[J] & ((1u << I) - 1u);
-  const int64_t* scp = reinterpret_cast<const int64_t*>(sm + cfg.o_scp);
-  const unsigned long long* spo = reinterpret_cast<const unsigned long long*>(sm + cfg.o_spo);
-  int rank[3];
-  bool act[3];
+  const int32_t* sslot = reinterpret_cast<const int32_t*>(sm + cfg.o_slot);
+  double* nzb = sink.nzval + *reinterpret_cast<const int64_t*>(sm + cfg.o_base);
 #pragma unroll
   for (int a1 = 0; a1 < 3; ++a1) {
-    const unsigned m = (unsigned)si[I_MASK + a1 + 3 * a2];
-    act[a1] = (m >> I) & 1u;
-    rank[a1] = popc8(m & rmask);
-  }
+    const int a = a1 + 3 * a2;
+    const unsigned m = (unsigned)si[I_MASK + a];
+    if (!((m >> I) & 1u)) continue;   // rows of inactive dofs are discarded
+    double* dst = nzb + popc8(m & rmask);
 #pragma unroll
-  for (int b = 0; b < 9; ++b) {
-    if (si[I_EQ + 8 * b + J] < 0) continue;  // columns exist only for active dofs (FiniteElement.jl:111)
-    const int64_t cp = scp[8 * b + J];
-#pragma unroll
-    for (int a1 = 0; a1 < 3; ++a1) {
-      if (!act[a1]) continue;
-      const int64_t slot = cp + (int64_t)((spo[9 * (a1 + 3 * a2) + b] >> (8 * J)) & 255ull) + rank[a1];
-      atomic_add(&sink.nzval[slot], acc[a1][b]);
+    for (int b = 0; b < 9; ++b) {
+      const int32_t rel = sslot[(9 * a + b) * 8 + J];
+      if (rel != SLOT_NONE) atomic_add(dst + rel, acc[a1][b]);
     }
   }
 }

@@ -125,7 +125,7 @@ inline Tables host_tables(const HostModel& M) {
   T.IX = M.IX0.data(); T.ID = M.ID0.data(); T.nodemask = M.sym.nodemask.data();
   T.uel1 = M.uel1.data(); T.uel2 = M.uel2.data(); T.line1 = M.line1.data(); T.line2 = M.line2.data();
   T.tdb = M.tdb.data(); T.colptr = M.sym.colptr.data(); T.elpair = M.sym.elpair.data();
-  T.pairoff = M.sym.pairoff.data(); T.numnp = M.numnp; T.numel = M.numel; T.num1el = M.num1el; T.nuel1 = M.nuel1;
+  T.pairoff = M.sym.pairoff.data(); T.eq0 = M.sym.eq0.data(); T.numnp = M.numnp; T.numel = M.numel; T.num1el = M.num1el; T.nuel1 = M.nuel1;
   return T;
 }
 inline BoundaryTables host_boundary_tables(const HostModel& M) {

@@ -27,6 +27,8 @@ struct Symbolic {
   std::vector<int64_t> n2e_ptr;    // numnp+1   node -> elements (ascending element id)
   std::vector<int32_t> n2e;        // 9 numel entries: element id
   std::vector<uint8_t> n2e_loc;    // local node index of the node in that element
+  std::vector<int32_t> eq0;        // numnp: first active equation at or after the node (nmdf if none): colptr[eq0[n]]
+                                   // is a lower bound of every column pointer of nodes >= n
 };
 
 template <class F> inline void parallel_for(int64_t n, F&& fn) {
@@ -91,6 +93,15 @@ inline void build_symbolic(Symbolic& S, int64_t numel, int64_t numnp, int ndf, i
     for (int d = 0; d < ndf; ++d)
       if (ID0[(int64_t)ndf * n + d] >= 0) m |= 1u << d;
     S.nodemask[n] = (uint8_t)m;
+  }
+  S.eq0.assign(numnp, (int32_t)nmdf);
+  {
+    int32_t next = (int32_t)nmdf;
+    for (int64_t n = numnp - 1; n >= 0; --n) {
+      for (int d = ndf - 1; d >= 0; --d)
+        if (ID0[(int64_t)ndf * n + d] >= 0) next = ID0[(int64_t)ndf * n + d];
+      S.eq0[n] = next;
+    }
   }
   S.pairoff.assign((size_t)S.npairs * 8, 0);
   std::vector<int64_t> colcount(nmdf + 1, 0);
