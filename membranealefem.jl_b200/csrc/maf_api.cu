@@ -54,6 +54,7 @@ area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __
     __syncthreads();
     phase_gauss<MOTION>(tid, cfg, dt, sm);
     __syncthreads();
+    if (tid >= MAF_NT - 32) prefetch_next(tid & 31, cfg, T, el + gridDim.x, xms, cps);
     if (st.kel == nullptr) {
       phase_residual(tid, MAF_NT, cfg, T, el, sm, r_gl, nullptr);
       KSink sink{nzval, nullptr, nullptr, 0};
@@ -410,6 +411,7 @@ int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* pa
     h->T.elpair = upload(h, M.sym.elpair.data(), M.sym.elpair.size());
     h->T.pairoff = upload(h, M.sym.pairoff.data(), M.sym.pairoff.size());
     h->T.eq0 = upload(h, M.sym.eq0.data(), M.sym.eq0.size());
+    h->T.utab = M.utab.empty() ? nullptr : upload(h, M.utab.data(), M.utab.size());
     h->T.numnp = M.numnp; h->T.numel = M.numel; h->T.num1el = M.num1el; h->T.nuel1 = M.nuel1;
     h->BT.edge1 = upload(h, M.edge1.data(), M.edge1.size());
     h->BT.edge2 = upload(h, M.edge2.data(), M.edge2.size());

@@ -226,15 +226,18 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   cfg.o_cm = o; o += 27;
   cfg.o_cl = o; o += 9;
   cfg.o_cp = o; o += 9;
-  cfg.o_w = o; o += 9;
-  cfg.o_phi = o; o += PHI_DOUBLES;
+  o += o & 1;
+  cfg.o_phi = o; o += PHI_DOUBLES;      // basis block: Phi | FG | w, contiguous (BASIS_DOUBLES)
   cfg.o_FG = o; o += 9 * FG_STRIDE;
+  cfg.o_w = o; o += 10;
   cfg.o_E = o; o += 9 * E_STRIDE;
   cfg.o_S = o; o += 9 * S_STRIDE;
   cfg.o_G = o; o += 9 * G_STRIDE;
-  cfg.o_int = o; o += (I_END + 1) / 2;
+  cfg.o_int = o; o += (I_PAIR + 1) / 2;   // node ids, equation numbers, active-dof masks
   o += o & 1;
-  cfg.o_slot = o; o += 81 * 8 / 2;
+  cfg.o_slot = o; o += 36;
+  cfg.o_po = o; o += 81;
+  o += o & 1;
   cfg.o_base = o; o += 2;
   cfg.o_A = o; o += 9 * cfg.asize;
   cfg.smem_doubles = o;

@@ -68,7 +68,7 @@ struct Config {
   Material mat;
   double dbscale;                 // adb / zv
   // shared-memory layout (offsets in doubles from the element's block)
-  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_G, o_A, o_int, o_slot, o_base, o_FG, smem_doubles;
+  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_G, o_A, o_int, o_slot, o_po, o_base, o_FG, smem_doubles;
 };
 
 // interpolated Gauss-point inputs E[gp][.]
@@ -94,13 +94,14 @@ struct Tables {
   const int32_t* elpair;    // numel x 81: index of (A = node a, B = node b) in the node-adjacency list of B
   const uint8_t* pairoff;   // npairs x 8: rows that precede node A's rows in column (B,J)
   const int32_t* eq0;       // numnp: an equation number whose column pointer bounds the node's columns from below
+  const double* utab;       // (nuel1*nuel2) x BASIS_DOUBLES precomputed basis blocks, or NULL (built per element)
   int64_t numnp, numel;
   int num1el, nuel1;
 };
 
 // shared-memory basis table: Phi[gp][c][a2][4] (node a = a1 + 3 a2 at 4 a2 + a1; the pad keeps the three values
 // of a node row 16-byte aligned so that they load as LDS.128 + LDS.64)
-enum { PHI_C = 12, PHI_GP = 72, PHI_DOUBLES = 9 * 72, FG_STRIDE = 18 };
+enum { PHI_C = 12, PHI_GP = 72, PHI_DOUBLES = 9 * 72, FG_STRIDE = 18, BASIS_DOUBLES = 9 * 72 + 9 * 18 + 10 };
 #define SLOT_NONE (-2147483647 - 1)
 MAF_HD int phi_a(int a) { return 4 * (a / 3) + (a % 3); }
 struct alignas(16) dbl2 { double x, y; };
@@ -119,6 +120,30 @@ MAF_HD int popc8(unsigned x) {
 #endif
 }
 
+// basis block of one (unique) element from its two 1-D tables l1, l2 ([gp][10] = w, N[3], dN[3], ddN[3]):
+//   Phi[gp][c][a2][4] : 2-D basis values, each ONE product of two 1-D entries (GpBasisFn.jl:102-110)
+//   FG[gp][18]        : the 1-D factors f[order][b1], g[order][b2] for the sum-factorised contraction
+//   w[gp]             : w1 * w2 (GpBasisFn.jl:106)
+MAF_HD void build_basis_block(int tid, int nt, const double* l1, const double* l2, double* out) {
+  for (int k = tid; k < 54 * 3; k += nt) {   // one (gp, channel, node row a2) per thread: three products
+    const int a2 = k % 3, c = (k / 3) % 6, gp = k / 18;
+    const int g1 = gp % 3, g2 = gp / 3;
+    // derivative orders per channel: N(0,0) N1(1,0) N2(0,1) N11(2,0) N22(0,2) N12(1,1)
+    const int o1 = (c == CH_N1 || c == CH_N12) ? 1 : (c == CH_N11 ? 2 : 0);
+    const int o2 = (c == CH_N2 || c == CH_N12) ? 1 : (c == CH_N22 ? 2 : 0);
+    const double* f = l1 + 10 * g1 + 1 + 3 * o1;
+    const double gv = l2[10 * g2 + 1 + 3 * o2 + a2];
+    double* dst = out + PHI_GP * gp + PHI_C * c + 4 * a2;
+    dst[0] = f[0] * gv; dst[1] = f[1] * gv; dst[2] = f[2] * gv; dst[3] = 0.0;
+  }
+  for (int k = tid; k < 9 * FG_STRIDE; k += nt) {
+    const int gp = k / FG_STRIDE, q = k % FG_STRIDE;
+    out[PHI_DOUBLES + k] = q < 9 ? l1[10 * (gp % 3) + 1 + q] : l2[10 * (gp / 3) + 1 + (q - 9)];
+  }
+  for (int gp = tid; gp < 10; gp += nt)
+    out[PHI_DOUBLES + 9 * FG_STRIDE + gp] = gp < 9 ? l1[10 * (gp % 3)] * l2[10 * (gp / 3)] : 0.0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Phase 0: gather the element's nodal data, integer maps and basis table into shared memory.
 // FiniteElement.jl:100-101 (xms_el, cps_el), Mesh.jl:311-319 (table lookup by unique element).
@@ -127,7 +152,7 @@ MAF_HD void phase_gather(int tid, int nt, const Config& cfg, const Tables& T, in
                          const double* cps, double* sm) {
   int32_t* si = reinterpret_cast<int32_t*>(sm + cfg.o_int);
   const int64_t np = T.numnp;
-  for (int k = tid; k < 9 * 14; k += nt) {
+  for (int k = tid; k < 9 * 13; k += nt) {
     const int a = k % 9, q = k / 9;
     const int64_t node = T.IX[9 * el + a];
     if (q < 3) {
@@ -144,53 +169,65 @@ MAF_HD void phase_gather(int tid, int nt, const Config& cfg, const Tables& T, in
     } else if (q == 11) {
       si[I_NODE + a] = (int32_t)node;
       si[I_MASK + a] = T.nodemask[node];
-    } else if (q == 12) {
-      for (int d = 0; d < 8; ++d) si[I_EQ + 8 * a + d] = d < cfg.ndf ? T.ID[(int64_t)cfg.ndf * node + d] : -1;
     } else {
-      for (int b = 0; b < 9; ++b) si[I_PAIR + 9 * a + b] = T.elpair[81 * el + 9 * a + b];
+      for (int d = 0; d < 8; ++d) si[I_EQ + 8 * a + d] = d < cfg.ndf ? T.ID[(int64_t)cfg.ndf * node + d] : -1;
     }
   }
-  // scatter map of this element, looked up once: slot of (first row of node a, column (b, J)) relative to the
-  // first column pointer of the element's first node  ->  sslot[(9 a + b) * 8 + J]   (int32)
-  int32_t* sslot = reinterpret_cast<int32_t*>(sm + cfg.o_slot);
+  // scatter map of this element, looked up once:
+  //   slot(a, I; b, J) = base + cprel[8 b + J] + po[(9 a + b) * 8 + J] + rank(I | a, J)
+  // base = a column pointer that bounds the element's columns from below, cprel = column pointer of (b, J)
+  // relative to it (int32; SLOT_NONE for a Dirichlet column), po = the pairoff row of the node pair (a, b).
+  int32_t* cprel = reinterpret_cast<int32_t*>(sm + cfg.o_slot);
+  unsigned long long* po = reinterpret_cast<unsigned long long*>(sm + cfg.o_po);
   const int64_t base = T.colptr[T.eq0[T.IX[9 * el]]];
-  for (int k = tid; k < 81 * 8; k += nt) {
-    const int J = k & 7, ab = k >> 3, b = ab % 9;
-    int32_t rel = SLOT_NONE;   // columns exist only for active dofs (FiniteElement.jl:111)
-    if (J < cfg.ndf) {
-      const int32_t eq = T.ID[(int64_t)cfg.ndf * T.IX[9 * el + b] + J];
-      if (eq >= 0) rel = (int32_t)(T.colptr[eq] - base) + (int32_t)T.pairoff[(int64_t)T.elpair[81 * el + ab] * 8 + J];
+  for (int k = tid; k < 72 + 81; k += nt) {
+    if (k < 72) {
+      const int b = k >> 3, J = k & 7;
+      int32_t rel = SLOT_NONE;   // columns exist only for active dofs (FiniteElement.jl:111)
+      if (J < cfg.ndf) {
+        const int32_t eq = T.ID[(int64_t)cfg.ndf * T.IX[9 * el + b] + J];
+        if (eq >= 0) rel = (int32_t)(T.colptr[eq] - base);
+      }
+      cprel[k] = rel;
+    } else {
+      po[k - 72] = *reinterpret_cast<const unsigned long long*>(T.pairoff + (int64_t)T.elpair[81 * el + (k - 72)] * 8);
     }
-    sslot[k] = rel;
   }
   if (tid == 0) *reinterpret_cast<int64_t*>(sm + cfg.o_base) = base;
-  // basis table of this element: Phi[gp][c][a] = (1-D factor dir 1) * (1-D factor dir 2), one product each
+  // basis block of this element: Phi[gp][c][a2][4] | FG[gp][18] | w[9]   (contiguous, BASIS_DOUBLES)
   const int e1 = (int)(el % T.num1el), e2 = (int)(el / T.num1el);
-  const double* l1 = T.line1 + 30 * T.uel1[e1];
-  const double* l2 = T.line2 + 30 * T.uel2[e2];
-  for (int k = tid; k < 54 * 3; k += nt) {   // one (gp, channel, node row a2) per thread: three products
-    const int a2 = k % 3, c = (k / 3) % 6, gp = k / 18;
-    const int g1 = gp % 3, g2 = gp / 3;
-    // derivative orders per channel: N(0,0) N1(1,0) N2(0,1) N11(2,0) N22(0,2) N12(1,1)
-    const int o1 = (c == CH_N1 || c == CH_N12) ? 1 : (c == CH_N11 ? 2 : 0);
-    const int o2 = (c == CH_N2 || c == CH_N12) ? 1 : (c == CH_N22 ? 2 : 0);
-    const double* f = l1 + 10 * g1 + 1 + 3 * o1;
-    const double gv = l2[10 * g2 + 1 + 3 * o2 + a2];
-    double* dst = sm + cfg.o_phi + PHI_GP * gp + PHI_C * c + 4 * a2;
-    dst[0] = f[0] * gv; dst[1] = f[1] * gv; dst[2] = f[2] * gv; dst[3] = 0.0;
+  if (T.utab) {   // precomputed per unique element (same products, formed once on the host): straight copy
+    const dbl2* src = reinterpret_cast<const dbl2*>(T.utab + (size_t)BASIS_DOUBLES * (T.uel1[e1] + (size_t)T.nuel1 * T.uel2[e2]));
+    dbl2* dst = reinterpret_cast<dbl2*>(sm + cfg.o_phi);
+    for (int k = tid; k < BASIS_DOUBLES / 2; k += nt) dst[k] = src[k];
+  } else {
+    build_basis_block(tid, nt, T.line1 + 30 * T.uel1[e1], T.line2 + 30 * T.uel2[e2], sm + cfg.o_phi);
   }
-  // 1-D factors per Gauss point for the sum-factorised second contraction: f[order][b1] (9), g[order][b2] (9)
-  for (int k = tid; k < 9 * FG_STRIDE; k += nt) {
-    const int gp = k / FG_STRIDE, q = k % FG_STRIDE;
-    sm[cfg.o_FG + k] = q < 9 ? l1[10 * (gp % 3) + 1 + q] : l2[10 * (gp / 3) + 1 + (q - 9)];
-  }
-  for (int gp = tid; gp < 9; gp += nt) sm[cfg.o_w + gp] = l1[10 * (gp % 3)] * l2[10 * (gp / 3)];
   // the closed-form columns of the Gauss-point tangent touch only a few rows: start from zero
   {
     dbl2* Az = reinterpret_cast<dbl2*>(sm + cfg.o_A);
     const dbl2 z = {0.0, 0.0};
     for (int k = tid; k < 9 * cfg.asize / 2; k += nt) Az[k] = z;
   }
+}
+
+// L2 prefetch of what the next element of this CTA will gather (device only; a no-op on the host)
+MAF_HD void prefetch_next(int lane, const Config& cfg, const Tables& T, int64_t el, const double* xms,
+                          const double* cps) {
+#if defined(__CUDA_ARCH__)
+  if (el >= T.numel) return;
+  if (lane < 9) {
+    const int64_t node = T.IX[9 * el + lane];
+    for (int q = 0; q < 3; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(xms + node + T.numnp * q));
+    for (int q = 0; q < cfg.ndf; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(cps + node + T.numnp * q));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(T.ID + (int64_t)cfg.ndf * node));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(T.nodemask + node));
+  } else if (lane < 13) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(T.elpair + 81 * el + 32 * (lane - 9)));
+  }
+#else
+  (void)lane; (void)cfg; (void)T; (void)el; (void)xms; (void)cps;
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -664,19 +701,24 @@ MAF_HD void phase_tangent_task(const Config& cfg, const Tables& T, int64_t el, i
   // atomics path: K_gl[LM[i], LM[j]] += K_el[i, j] for active rows and columns (FiniteElement.jl:129-136)
   const int I = cfg.fdof[f][i], J = cfg.fdof[g][j];
   const unsigned rmask = cfg.rowmask[J] & ((1u << I) - 1u);
-  const int32_t* sslot = reinterpret_cast<const int32_t*>(sm + cfg.o_slot);
+  const int32_t* cprel = reinterpret_cast<const int32_t*>(sm + cfg.o_slot);
+  const uint8_t* po8 = reinterpret_cast<const uint8_t*>(sm + cfg.o_po);
   double* nzb = sink.nzval + *reinterpret_cast<const int64_t*>(sm + cfg.o_base);
+  double* dst[3];
+  bool act[3];
 #pragma unroll
   for (int a1 = 0; a1 < 3; ++a1) {
-    const int a = a1 + 3 * a2;
-    const unsigned m = (unsigned)si[I_MASK + a];
-    if (!((m >> I) & 1u)) continue;   // rows of inactive dofs are discarded
-    double* dst = nzb + popc8(m & rmask);
+    const unsigned m = (unsigned)si[I_MASK + a1 + 3 * a2];
+    act[a1] = (m >> I) & 1u;            // rows of inactive dofs are discarded
+    dst[a1] = nzb + popc8(m & rmask);
+  }
 #pragma unroll
-    for (int b = 0; b < 9; ++b) {
-      const int32_t rel = sslot[(9 * a + b) * 8 + J];
-      if (rel != SLOT_NONE) atomic_add(dst + rel, acc[a1][b]);
-    }
+  for (int b = 0; b < 9; ++b) {
+    const int32_t rel = cprel[8 * b + J];
+    if (rel == SLOT_NONE) continue;
+#pragma unroll
+    for (int a1 = 0; a1 < 3; ++a1)
+      if (act[a1]) atomic_add(dst[a1] + rel + po8[(9 * (a1 + 3 * a2) + b) * 8 + J], acc[a1][b]);
   }
 }
 

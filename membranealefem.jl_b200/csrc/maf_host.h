@@ -22,7 +22,7 @@ struct HostModel {
   int64_t numel = 0, numnp = 0, nmdf = 0;
   int ndf = 0, num1el = 0, num2el = 0, nuel1 = 0, nuel2 = 0, motion = 0, scenario = 0, pattern_mode = 0;
   std::vector<int32_t> IX0, ID0, uel1, uel2;
-  std::vector<double> line1, line2, edge1, edge2, tdb;
+  std::vector<double> line1, line2, edge1, edge2, tdb, utab;
   std::vector<int32_t> b_elems, b_offs, b_bdry, b_type;
   std::vector<double> b_val;
   int n_neu = 0;
@@ -97,6 +97,14 @@ inline void build_host_model(HostModel& M, const maf_mesh_desc* d, const maf_par
                p->pattern_mode == MAF_PATTERN_SYM, nthreads);
   build_symbolic(M.sym, M.numel, M.numnp, M.ndf, M.nmdf, M.IX0.data(), M.ID0.data(), M.cfg.rowmask);
   build_tdb(M.nuel1, M.nuel2, M.line1.data(), M.line2.data(), d->xi, M.tdb);
+  // basis blocks per unique element (skipped when the knot vectors are so irregular that the table would be large)
+  if ((int64_t)M.nuel1 * M.nuel2 <= 4096) {
+    M.utab.assign((size_t)M.nuel1 * M.nuel2 * BASIS_DOUBLES, 0.0);
+    for (int u2 = 0; u2 < M.nuel2; ++u2)
+      for (int u1 = 0; u1 < M.nuel1; ++u1)
+        build_basis_block(0, 1, M.line1.data() + 30 * u1, M.line2.data() + 30 * u2,
+                          M.utab.data() + (size_t)BASIS_DOUBLES * (u1 + (size_t)M.nuel1 * u2));
+  }
 
   // Neumann conditions in the reference's order (FiniteElement.jl:151-154)
   M.n_neu = d->n_neu;
@@ -125,7 +133,7 @@ inline Tables host_tables(const HostModel& M) {
   T.IX = M.IX0.data(); T.ID = M.ID0.data(); T.nodemask = M.sym.nodemask.data();
   T.uel1 = M.uel1.data(); T.uel2 = M.uel2.data(); T.line1 = M.line1.data(); T.line2 = M.line2.data();
   T.tdb = M.tdb.data(); T.colptr = M.sym.colptr.data(); T.elpair = M.sym.elpair.data();
-  T.pairoff = M.sym.pairoff.data(); T.eq0 = M.sym.eq0.data(); T.numnp = M.numnp; T.numel = M.numel; T.num1el = M.num1el; T.nuel1 = M.nuel1;
+  T.pairoff = M.sym.pairoff.data(); T.eq0 = M.sym.eq0.data(); T.utab = M.utab.empty() ? nullptr : M.utab.data(); T.numnp = M.numnp; T.numel = M.numel; T.num1el = M.num1el; T.nuel1 = M.nuel1;
   return T;
 }
 inline BoundaryTables host_boundary_tables(const HostModel& M) {
