@@ -195,10 +195,10 @@ def main():
     dt = 0.5
 
     # strips of element rows
+    part = maf.pkg.host.partition
     if world > 1:
-        r0 = (rank * a.n) // world
-        r1 = ((rank + 1) * a.n) // world
-        asm.set_element_range(r0 * a.n + 1, r1 * a.n)
+        e_first, e_last = part.strip_elements(a.n, a.n, world, rank)
+        asm.set_element_range(e_first, e_last)
     info = asm.range_info()
     my_elems = info["elements"][1] - info["elements"][0] + 1
 
@@ -209,42 +209,18 @@ def main():
     d_n = torch.zeros(1, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
-    # interface overlaps with the neighbouring strips (1-based inclusive -> python slices)
-    nbrs = []
+    exchange = None
     if world > 1:
         mine = torch.tensor([info["rows"][0], info["rows"][1], info["slots"][0], info["slots"][1]], device=dev)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        allr = [t.tolist() for t in allr]
-        for nb in (rank - 1, rank + 1):
-            if 0 <= nb < world:
-                lo_r, hi_r = max(allr[rank][0], allr[nb][0]), min(allr[rank][1], allr[nb][1])
-                lo_s, hi_s = max(allr[rank][2], allr[nb][2]), min(allr[rank][3], allr[nb][3])
-                nr, ns = max(0, hi_r - lo_r + 1), max(0, hi_s - lo_s + 1)
-                nbrs.append((nb, slice(lo_r - 1, lo_r - 1 + nr), slice(lo_s - 1, lo_s - 1 + ns),
-                             torch.empty(nr + ns, dtype=torch.float64, device=dev),
-                             torch.empty(nr + ns, dtype=torch.float64, device=dev)))
-        own_rows = slice(info["rows"][0] - 1 if rank == 0 else allr[rank - 1][1], info["rows"][1])
+        exchange = part.InterfaceExchange(dist, [t.tolist() for t in allr], rank, d_r)
 
     def step():
         asm.assemble_device(d_x.data_ptr(), d_c.data_ptr(), dt, dt, scatter_mode=mode, d_r=d_r.data_ptr(),
                             d_nzval=d_k.data_ptr(), d_rnorm2=d_n.data_ptr() if world == 1 else None, stream=stream)
-        if world > 1:
-            ops = []
-            for (nb, sr, sk, sbuf, rbuf) in nbrs:
-                nr = sr.stop - sr.start
-                sbuf[:nr].copy_(d_r[sr])
-                sbuf[nr:].copy_(d_k[sk])
-                ops.append(dist.P2POp(dist.isend, sbuf, nb))
-                ops.append(dist.P2POp(dist.irecv, rbuf, nb))
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-            for (nb, sr, sk, sbuf, rbuf) in nbrs:
-                nr = sr.stop - sr.start
-                d_r[sr] += rbuf[:nr]
-                d_k[sk] += rbuf[nr:]
-            d_n[0] = (d_r[own_rows] ** 2).sum()
-            dist.all_reduce(d_n)
+        if exchange is not None:
+            exchange(d_r, d_k, d_n)   # interface rows/entries to the neighbours (NCCL send/recv) + all-reduce |r|^2
 
     def barrier():
         torch.cuda.synchronize()
@@ -345,8 +321,9 @@ def main():
                       "numel": mesh.numel, "numnp": mesh.numnp, "nmdf": mesh.nmdf, "nnz": asm.nnz,
                       "pattern": "P_blk", "scatter": a.scatter, "elements_per_rank": my_elems,
                       "l2": "no flush: each step streams r + nzval (%.1f GB) >> 126 MB L2" % (asm.nnz * 8 / 1e9),
-                      "parallelism": f"{world} strip(s) of element rows; NCCL send/recv of interface rows + all-reduce "
-                                     "of the residual norm" if world > 1 else "single GPU",
+                      "parallelism": (f"{world} strips of element rows; NCCL send/recv of interface rows + all-reduce "
+                                      f"of the residual norm ({exchange.bytes_per_step()} B/step/rank)")
+                      if world > 1 else "single GPU",
                       "setup_s": t_setup, "kernel": asm.kernel_info()},
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
            "rnorm2": rnorm2}

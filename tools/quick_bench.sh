@@ -1,8 +1,8 @@
 #!/bin/bash
-# usage: tools/quick_bench.sh <tag> [lib]  -> prints one summary line, writes gpurun_out/<tag>.json
-tag=$1; lib=$2
-if [ -n "$lib" ]; then export MAF_LIB=$lib; fi
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/$tag.json 2> gpurun_out/$tag.err
+# usage: tools/quick_bench.sh <tag> [lib] [extra bench args]  -> prints one summary line, writes gpurun_out/<tag>.json
+tag=$1; lib=$2; shift; shift
+if [ -n "$lib" ] && [ "$lib" != "-" ]; then export MAF_LIB=$lib; fi
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e "$@" > gpurun_out/$tag.json 2> gpurun_out/$tag.err
 python - <<PY
 import json
 try:
