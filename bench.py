@@ -311,8 +311,14 @@ def run(a, out_stream):
     fp64_peak = maf.fp64_peak_tflops(local_rank)
     ach_gbs = my_elems * B_EL[a.motion] / (area * 1e-3) / 1e9
     ach_tf = my_elems * F_EL[a.motion] / (area * 1e-3) / 1e12
+    # DRAM bytes of one launch of this kernel on this workload, from the committed `ncu --set full` capture
+    traffic, traffic_src = None, None
+    tfile = os.path.join(ROOT, "profiles", "r1_area_kernel_alevb_1001_traffic.json")
+    if a.motion == "ALEVB" and a.n == 1001 and a.scatter == "atomic" and world == 1 and os.path.exists(tfile):
+        tj = json.load(open(tfile))
+        traffic, traffic_src = tj["dram_read"] + tj["dram_write"], "profiles/r1_area_kernel_alevb_1001_full.txt"
     roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                "traffic": None, "kernel": f"area_kernel<{a.motion}>", "kernel_ms": area,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": f"area_kernel<{a.motion}>", "kernel_ms": area,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_element": B_EL[a.motion],
                 "fp64": {"achieved_tflops": ach_tf, "peak_tflops": fp64_peak, "frac": ach_tf / fp64_peak,
@@ -330,7 +336,7 @@ def run(a, out_stream):
            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"synthetic flat F_PULL patch {a.n}x{a.n} = {mesh.numel} elements, {a.motion} "
-                                  f"(ndf {mesh.ndf}), perturbed state (SURVEY 8(d)5), uniform-knot... see knots",
+                                  f"(ndf {mesh.ndf}), perturbed state (SURVEY 8(d)5)",
                       "knots": "reference rule (Mesh.jl:176-181): centre-refined knots for >= 18 elements/direction",
                       "numel": mesh.numel, "numnp": mesh.numnp, "nmdf": mesh.nmdf, "nnz": asm.nnz,
                       "pattern": "P_blk", "scatter": a.scatter, "elements_per_rank": my_elems,

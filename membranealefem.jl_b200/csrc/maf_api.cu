@@ -44,17 +44,19 @@ template <int MOTION>
 __global__ void __launch_bounds__(MAF_NT, MAF_MIN_CTAS)
 area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __restrict__ xms,
             const double* __restrict__ cps, double dt, double* __restrict__ r_gl, double* __restrict__ nzval,
-            const StageSink st, int64_t e0, int64_t e1) {
+            const StageSink st, const int32_t* __restrict__ order, int64_t e0, int64_t e1) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
-  for (int64_t el = e0 + blockIdx.x; el < e1; el += gridDim.x) {
+  const int64_t ne = e1 - e0;
+  for (int64_t k = blockIdx.x; k < ne; k += gridDim.x) {
+    const int64_t el = order[k];
     phase_gather(tid, MAF_NT, cfg, T, el, xms, cps, sm);
     __syncthreads();
     phase_interp(tid, MAF_NT, cfg, sm);
     __syncthreads();
     phase_gauss<MOTION>(tid, cfg, dt, sm);
     __syncthreads();
-    if (tid >= MAF_NT - 32) prefetch_next(tid & 31, cfg, T, el + gridDim.x, xms, cps);
+    if (tid >= MAF_NT - 32 && k + gridDim.x < ne) prefetch_next(tid & 31, cfg, T, order[k + gridDim.x], xms, cps);
     if (st.kel == nullptr) {
       phase_residual(tid, MAF_NT, cfg, T, el, sm, r_gl, nullptr);
       KSink sink{nzval, nullptr, nullptr, 0};
@@ -162,6 +164,7 @@ struct maf_handle {
   GatherTables G{};
   bool gather_ready = false;
   int16_t* d_task_ij = nullptr;
+  int32_t* d_order = nullptr;   // processing order of the elements of [e0, e1)
   int nij = 0;
   double *d_xms = nullptr, *d_cps = nullptr, *d_r = nullptr, *d_nz = nullptr, *d_rn = nullptr, *d_part = nullptr;
   double *d_kel = nullptr, *d_rel = nullptr;
@@ -201,7 +204,7 @@ template <class Tp> static Tp* dalloc(maf_handle* h, size_t n) {
 }
 
 typedef void (*area_fn)(const Config, const Tables, const double*, const double*, double, double*, double*,
-                        const StageSink, int64_t, int64_t);
+                        const StageSink, const int32_t*, int64_t, int64_t);
 static area_fn area_kernel_of(int motion) {
   switch (motion) {
     case M_STATIC: return area_kernel<M_STATIC>;
@@ -231,6 +234,11 @@ static void compute_ranges(maf_handle* h) {
   h->eq_hi = eq_hi;
   h->slot_lo = M.sym.colptr[eq_lo];
   h->slot_hi = M.sym.colptr[eq_hi];
+  std::vector<int32_t> order;
+  build_element_order(M.num1el, h->e0, h->e1, order);
+  if (h->d_order) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFree(h->d_order)); h->d_order = nullptr; }
+  CU(cudaMalloc(&h->d_order, std::max<size_t>(order.size(), 1) * sizeof(int32_t)));
+  if (!order.empty()) CU(cudaMemcpy(h->d_order, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
 }
 
 static void ensure_gather(maf_handle* h) {
@@ -247,6 +255,8 @@ static void ensure_gather(maf_handle* h) {
   h->G.n2e = upload(h, S.n2e.data(), S.n2e.size());
   h->G.n2e_loc = upload(h, S.n2e_loc.data(), S.n2e_loc.size());
   h->G.ij_of = upload(h, GH.ij_of.data(), GH.ij_of.size());
+  fill_gather_tables(GH, h->G);
+  if (GH.nij > MAF_MAX_NIJ) throw std::runtime_error("too many dof-block classes for the gather kernel");
   h->G.npairs = S.npairs;
   h->d_task_ij = upload(h, GH.task_ij.data(), GH.task_ij.size());
   h->gather_ready = true;
@@ -297,7 +307,7 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
   }
   CU(cudaEventRecord(h->ev[6], s));
   if (ne > 0) {
-    kern<<<grid, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, h->e0, h->e1);
+    kern<<<grid, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, h->d_order, h->e0, h->e1);
     CU(cudaGetLastError());
     h->launches += 1;
   }
@@ -459,6 +469,7 @@ int maf_destroy(maf_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->d_order) cudaFree(h->d_order);
   if (h->d_kel) cudaFree(h->d_kel);
   if (h->d_rel) cudaFree(h->d_rel);
   if (h->h_pin_in) cudaFreeHost(h->h_pin_in);

@@ -108,7 +108,16 @@ struct alignas(16) dbl2 { double x, y; };
 MAF_HD dbl2 ld2(const double* p) { return *reinterpret_cast<const dbl2*>(p); }
 
 #if defined(__CUDA_ARCH__)
+#if defined(MAF_RED_EVICT_LAST)
+// FP64 reduction with an L2 evict_last hint: the slot will be hit again by the neighbouring elements
+MAF_HD void atomic_add(double* p, double v) {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+#else
 MAF_HD void atomic_add(double* p, double v) { atomicAdd(p, v); }
+#endif
 #else
 MAF_HD void atomic_add(double* p, double v) { *p += v; }
 #endif

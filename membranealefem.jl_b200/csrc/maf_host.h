@@ -152,24 +152,62 @@ inline double neumann_value(int ntype, double nval, double time, double bend_tm)
 struct GatherHost {
   std::vector<int32_t> pair_node;
   std::vector<int16_t> ij_of, task_ij;
-  int nij = 0;
+  uint8_t class_I[64], class_J[64];
+  int nij = 0, sym_fill = 0;
 };
 inline void build_gather_host(const HostModel& M, GatherHost& GH) {
   const Symbolic& S = M.sym;
   GH.pair_node.resize(S.npairs);
   for (int64_t B = 0; B < M.numnp; ++B)
     for (int64_t p = S.nbr_ptr[B]; p < S.nbr_ptr[B + 1]; ++p) GH.pair_node[p] = (int32_t)B;
-  // (I,J) classes = distinct (row dof, col dof) pairs that own tangent tasks
-  GH.ij_of.assign(64, -1);
-  GH.task_ij.assign(M.cfg.ntasks, -1);
-  GH.nij = 0;
+  // (I,J) classes = distinct (row dof, col dof) pairs that own tangent tasks, in destination order (J, then I)
+  bool has[8][8] = {};
   for (int t = 0; t < M.cfg.ntasks; ++t) {
     const Task& tk = M.cfg.tasks[t];
     const Block& bk = M.cfg.blocks[tk.blk];
-    const int I = M.cfg.fdof[bk.f][tk.i], J = M.cfg.fdof[bk.g][tk.j];
-    if (GH.ij_of[8 * I + J] < 0) GH.ij_of[8 * I + J] = (int16_t)GH.nij++;
-    GH.task_ij[t] = GH.ij_of[8 * I + J];
+    has[M.cfg.fdof[bk.f][tk.i]][M.cfg.fdof[bk.g][tk.j]] = true;
   }
+  GH.ij_of.assign(64, -1);
+  GH.nij = 0;
+  for (int J = 0; J < 8; ++J)
+    for (int I = 0; I < 8; ++I)
+      if (has[I][J]) {
+        GH.class_I[GH.nij] = (uint8_t)I;
+        GH.class_J[GH.nij] = (uint8_t)J;
+        GH.ij_of[8 * I + J] = (int16_t)GH.nij++;
+      }
+  GH.task_ij.assign(M.cfg.ntasks, -1);
+  for (int t = 0; t < M.cfg.ntasks; ++t) {
+    const Task& tk = M.cfg.tasks[t];
+    const Block& bk = M.cfg.blocks[tk.blk];
+    GH.task_ij[t] = GH.ij_of[8 * M.cfg.fdof[bk.f][tk.i] + M.cfg.fdof[bk.g][tk.j]];
+  }
+  GH.sym_fill = M.pattern_mode == MAF_PATTERN_SYM ? 1 : 0;
+}
+inline void fill_gather_tables(const GatherHost& GH, GatherTables& G) {
+  for (int c = 0; c < 64; ++c) { G.class_I[c] = GH.class_I[c]; G.class_J[c] = GH.class_J[c]; }
+  G.sym_fill = GH.sym_fill;
+}
+
+// processing order of the elements of a range: Z-order (Morton) over (e1, e2), so that the elements a wave of CTAs
+// works on at the same time form a compact 2-D patch and the contributions to an nnz slot / the reads of a node
+// arrive while the line is still in L2 (a row-major sweep re-fetches every nzval sector once per element row)
+inline void build_element_order(int num1el, int64_t e0, int64_t e1, std::vector<int32_t>& order) {
+  auto spread = [](uint64_t v) {
+    v &= 0xffffffffull;
+    v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+    v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+  };
+  std::vector<std::pair<uint64_t, int32_t>> key((size_t)(e1 - e0));
+  for (int64_t e = e0; e < e1; ++e)
+    key[(size_t)(e - e0)] = {spread((uint64_t)(e % num1el)) | (spread((uint64_t)(e / num1el)) << 1), (int32_t)e};
+  std::sort(key.begin(), key.end());
+  order.resize(key.size());
+  for (size_t k = 0; k < key.size(); ++k) order[k] = key[k].second;
 }
 
 }  // namespace maf

@@ -18,7 +18,10 @@ static void run_area(const HostModel& M, const Tables& T, const double* xms, con
   const Config& cfg = M.cfg;
   const int nt = cfg.nthreads;
   std::vector<double> sm(cfg.smem_doubles);
-  for (int64_t el = e0; el < e1; ++el) {
+  std::vector<int32_t> order;
+  build_element_order(M.num1el, e0, e1, order);
+  for (size_t k = 0; k < order.size(); ++k) {
+    const int64_t el = order[k];
     std::fill(sm.begin(), sm.end(), std::nan(""));  // any read of an unwritten slot poisons the result
     for (int t = 0; t < nt; ++t) phase_gather(t, nt, cfg, T, el, xms, cps, sm.data());
     for (int t = 0; t < nt; ++t) phase_interp(t, nt, cfg, sm.data());
@@ -94,6 +97,7 @@ int emu_assemble(void* h, const double* xms, const double* cps, double time, dou
       G.nbr_ptr = M.sym.nbr_ptr.data(); G.nbr = M.sym.nbr.data(); G.pair_node = GH.pair_node.data();
       G.n2e_ptr = M.sym.n2e_ptr.data(); G.n2e = M.sym.n2e.data(); G.n2e_loc = M.sym.n2e_loc.data();
       G.ij_of = GH.ij_of.data(); G.npairs = M.sym.npairs;
+      fill_gather_tables(GH, G);
       for (int64_t p = 0; p < G.npairs; ++p) gather_K_pair(p, M.cfg, T, G, kel.data(), GH.nij, e0, e1, nzval);
       for (int64_t k = 0; k < M.numnp * M.ndf; ++k) gather_r_row(k, M.cfg, T, G, rel.data(), e0, e1, r);
     }
