@@ -45,29 +45,40 @@ __global__ void __launch_bounds__(MAF_NT, MAF_MIN_CTAS)
 area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __restrict__ xms,
             const double* __restrict__ cps, double dt, double* __restrict__ r_gl, double* __restrict__ nzval,
             const StageSink st, const int32_t* __restrict__ order, int64_t e0, int64_t e1) {
-  extern __shared__ double sm[];
+  extern __shared__ double smem_all[];
   const int tid = threadIdx.x;
   const int64_t ne = e1 - e0;
-  for (int64_t k = blockIdx.x; k < ne; k += gridDim.x) {
+  const int nfront = cfg.front_doubles;
+  double* sm = smem_all + 2 * nfront;   // back block: E, S, G, A
+  // software pipeline over the elements of this CTA: while element k is contracted (the longest phase), the last
+  // warp first gathers element k + gridDim.x into the other front buffer, so the dependent global loads of the
+  // gather (IX -> ID -> colptr, elpair -> pairoff) are off the critical path of the CTA. (Gathering during the
+  // shorter interpolate/Gauss window with named barriers was measured slower: profiles/r1_notes.md.)
+  if ((int64_t)blockIdx.x < ne) phase_gather(tid, MAF_NT, cfg, T, order[blockIdx.x], xms, cps, smem_all);
+  int cur = 0;
+  for (int64_t k = blockIdx.x; k < ne; k += gridDim.x, cur ^= 1) {
     const int64_t el = order[k];
-    phase_gather(tid, MAF_NT, cfg, T, el, xms, cps, sm);
+    const double* fr = smem_all + cur * nfront;
+    __syncthreads();   // front buffer `cur` complete; back block and front buffer `cur ^ 1` free
+    phase_interp(tid, MAF_NT, cfg, fr, sm);
     __syncthreads();
-    phase_interp(tid, MAF_NT, cfg, sm);
+    phase_gauss<MOTION>(tid, cfg, dt, fr, sm);
     __syncthreads();
-    phase_gauss<MOTION>(tid, cfg, dt, sm);
-    __syncthreads();
-    if (tid >= MAF_NT - 32 && k + gridDim.x < ne) prefetch_next(tid & 31, cfg, T, order[k + gridDim.x], xms, cps);
+    const int64_t kn = k + gridDim.x;
+    if (tid >= MAF_NT - 32 && kn < ne) {
+      phase_gather(tid & 31, 32, cfg, T, order[kn], xms, cps, smem_all + (cur ^ 1) * nfront);
+      if (kn + gridDim.x < ne) prefetch_next(tid & 31, cfg, T, order[kn + gridDim.x], xms, cps);
+    }
     if (st.kel == nullptr) {
-      phase_residual(tid, MAF_NT, cfg, T, el, sm, r_gl, nullptr);
+      phase_residual(tid, MAF_NT, cfg, fr, sm, r_gl, nullptr);
       KSink sink{nzval, nullptr, nullptr, 0};
-      phase_tangent(tid, cfg, T, el, sm, sink);
+      phase_tangent(tid, cfg, fr, sm, sink);
     } else {
       const int64_t le = el - e0;
-      phase_residual(tid, MAF_NT, cfg, T, el, sm, nullptr, st.rel + 72 * le);
+      phase_residual(tid, MAF_NT, cfg, fr, sm, nullptr, st.rel + 72 * le);
       KSink sink{nullptr, st.kel + (size_t)81 * st.nij * le, st.task_ij, st.nij};
-      phase_tangent(tid, cfg, T, el, sm, sink);
+      phase_tangent(tid, cfg, fr, sm, sink);
     }
-    __syncthreads();
   }
 }
 

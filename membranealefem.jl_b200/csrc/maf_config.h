@@ -153,8 +153,11 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   // into warp-sized chunks and each chunk is given to the least-loaded warp (longest-processing-time first):
   // the lanes of a warp never diverge on the class, and the warps of the CTA finish at about the same time.
   const int nwarps = nthreads / 32;
-  auto schedule = [&](const std::vector<int>& cls, const std::vector<int>& cost, int16_t* slot, int& rounds) {
-    struct Chunk { int cost; std::vector<int> ids; };
+  // `pin_cls` (if >= 0) is placed on the last warp and nothing else is (used for the Gauss phase, where the last
+  // warp first gathers the next element and then only runs the cheap LIN items)
+  auto schedule = [&](const std::vector<int>& cls, const std::vector<int>& cost, const std::vector<int>& init_load,
+                      int pin_cls, int16_t* slot, int& rounds) {
+    struct Chunk { int cost, cls; std::vector<int> ids; };
     std::vector<Chunk> chunks;
     for (size_t k = 0; k < cls.size();) {
       size_t e = k;
@@ -163,18 +166,22 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
       for (int q = 0; q < parts; ++q) {
         Chunk ch;
         ch.cost = cost[k];
+        ch.cls = cls[k];
         for (size_t t = k + (size_t)q * per; t < std::min(e, k + (size_t)(q + 1) * per); ++t) ch.ids.push_back((int)t);
         chunks.push_back(ch);
       }
       k = e;
     }
     std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& x, const Chunk& y) { return x.cost > y.cost; });
-    std::vector<int> load(nwarps, 0);
+    std::vector<int> load(init_load.begin(), init_load.end());
+    load.resize(nwarps, 0);
     std::vector<std::vector<const Chunk*>> plan(nwarps);
     for (const Chunk& ch : chunks) {
       int wbest = 0;
-      for (int w = 1; w < nwarps; ++w)
+      const int wlim = pin_cls >= 0 ? nwarps - 1 : nwarps;
+      for (int w = 1; w < wlim; ++w)
         if (load[w] < load[wbest]) wbest = w;
+      if (pin_cls >= 0 && ch.cls == pin_cls) wbest = nwarps - 1;
       plan[wbest].push_back(&ch);
       load[wbest] += ch.cost;
     }
@@ -193,7 +200,7 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
       cls[k] = cfg.items[k].type;
       cost[k] = cfg.items[k].type == IT_LIN ? 6 : 10;
     }
-    schedule(cls, cost, cfg.item_slot, cfg.item_rounds);
+    schedule(cls, cost, {}, -1, cfg.item_slot, cfg.item_rounds);
   }
   {
     std::vector<int> cls(cfg.ntasks), cost(cfg.ntasks);
@@ -201,7 +208,12 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
       cls[k] = cfg.blocks[cfg.tasks[k].blk].kind;
       cost[k] = kind_cost(cls[k]);
     }
-    schedule(cls, cost, cfg.task_slot, cfg.task_rounds);
+    // during the tangent phase the first warps also form the element residual (72 rows over the first 72 threads):
+    // account for that work when balancing the warps
+    std::vector<int> init(nwarps, 0);
+    for (int w = 0; w < nwarps && w < 3; ++w) init[w] = 60;
+    init[nwarps - 1] += 130;   // the last warp gathers the next element during the tangent phase
+    schedule(cls, cost, init, -1, cfg.task_slot, cfg.task_rounds);
   }
 
   // rows present in the pattern of a column of dof J
@@ -219,7 +231,8 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
       cfg.rowmask[J] = (uint8_t)m;
     }
 
-  // shared-memory layout (doubles)
+  // shared-memory layout (doubles). Front block (what the gather phase writes; double buffered so that the
+  // next element is gathered while the current one is contracted): offsets relative to the front block.
   int o = 0;
   cfg.o_x = o; o += 27;
   cfg.o_cv = o; o += 27;
@@ -227,22 +240,28 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   cfg.o_cl = o; o += 9;
   cfg.o_cp = o; o += 9;
   o += o & 1;
-  cfg.o_phi = o; o += PHI_DOUBLES;      // basis block: Phi | FG | w, contiguous (BASIS_DOUBLES)
+  cfg.o_phi = o; o += PHI_DOUBLES;      // basis block: Phi | FG | w | tdb, contiguous (BASIS_DOUBLES)
   cfg.o_FG = o; o += 9 * FG_STRIDE;
   cfg.o_w = o; o += 10;
-  cfg.o_E = o; o += 9 * E_STRIDE;
-  cfg.o_S = o; o += 9 * S_STRIDE;
-  cfg.o_G = o; o += 9 * G_STRIDE;
+  cfg.o_tdb = o; o += 82;
   cfg.o_int = o; o += (I_PAIR + 1) / 2;   // node ids, equation numbers, active-dof masks
   o += o & 1;
   cfg.o_slot = o; o += 36;
   cfg.o_po = o; o += 81;
   o += o & 1;
   cfg.o_base = o; o += 2;
+  cfg.front_doubles = o;
+  // back block (offsets relative to sm + 2 * front_doubles)
+  o = 0;
+  cfg.o_E = o; o += 9 * E_STRIDE;
+  cfg.o_S = o; o += 9 * S_STRIDE;
+  cfg.o_G = o; o += 9 * G_STRIDE;
+  o += o & 1;
   cfg.o_A = o; o += 9 * cfg.asize;
-  cfg.smem_doubles = o;
+  cfg.smem_doubles = 2 * cfg.front_doubles + o;
   // everything that is read with 16-byte loads must sit on an even double offset
-  bool ok = !(cfg.o_A & 1) && !(cfg.o_phi & 1) && !(cfg.o_FG & 1) && !(cfg.asize & 1) && !(cfg.o_base & 1);
+  bool ok = !(cfg.o_A & 1) && !(cfg.o_phi & 1) && !(cfg.o_FG & 1) && !(cfg.asize & 1) && !(cfg.o_base & 1) &&
+            !(cfg.front_doubles & 1) && !(cfg.o_po & 1);
   for (int f = 0; f < NFIELD; ++f) {
     ok = ok && !(cfg.aoff[f] & 1) && !(cfg.ald[f] & 1) && (cfg.bcol[f] < 0 || !(cfg.bcol[f] & 1));
     for (int g = 0; g < NFIELD; ++g)

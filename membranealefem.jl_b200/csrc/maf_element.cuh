@@ -68,7 +68,7 @@ struct Config {
   Material mat;
   double dbscale;                 // adb / zv
   // shared-memory layout (offsets in doubles from the element's block)
-  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_G, o_A, o_int, o_slot, o_po, o_base, o_FG, smem_doubles;
+  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_G, o_A, o_int, o_slot, o_po, o_base, o_FG, o_tdb, front_doubles, smem_doubles;
 };
 
 // interpolated Gauss-point inputs E[gp][.]
@@ -101,7 +101,7 @@ struct Tables {
 
 // shared-memory basis table: Phi[gp][c][a2][4] (node a = a1 + 3 a2 at 4 a2 + a1; the pad keeps the three values
 // of a node row 16-byte aligned so that they load as LDS.128 + LDS.64)
-enum { PHI_C = 12, PHI_GP = 72, PHI_DOUBLES = 9 * 72, FG_STRIDE = 18, BASIS_DOUBLES = 9 * 72 + 9 * 18 + 10 };
+enum { PHI_C = 12, PHI_GP = 72, PHI_DOUBLES = 9 * 72, FG_STRIDE = 18, BASIS_DOUBLES = 9 * 72 + 9 * 18 + 10 + 82 };  // Phi | FG | w | tdb
 #define SLOT_NONE (-2147483647 - 1)
 MAF_HD int phi_a(int a) { return 4 * (a / 3) + (a % 3); }
 struct alignas(16) dbl2 { double x, y; };
@@ -133,7 +133,8 @@ MAF_HD int popc8(unsigned x) {
 //   Phi[gp][c][a2][4] : 2-D basis values, each ONE product of two 1-D entries (GpBasisFn.jl:102-110)
 //   FG[gp][18]        : the 1-D factors f[order][b1], g[order][b2] for the sum-factorised contraction
 //   w[gp]             : w1 * w2 (GpBasisFn.jl:106)
-MAF_HD void build_basis_block(int tid, int nt, const double* l1, const double* l2, double* out) {
+MAF_HD void build_basis_block(int tid, int nt, const double* l1, const double* l2, const double* tdb, double* out) {
+  for (int k = tid; k < 82; k += nt) out[PHI_DOUBLES + 9 * FG_STRIDE + 10 + k] = k < 81 ? tdb[k] : 0.0;
   for (int k = tid; k < 54 * 3; k += nt) {   // one (gp, channel, node row a2) per thread: three products
     const int a2 = k % 3, c = (k / 3) % 6, gp = k / 18;
     const int g1 = gp % 3, g2 = gp / 3;
@@ -158,14 +159,14 @@ MAF_HD void build_basis_block(int tid, int nt, const double* l1, const double* l
 // FiniteElement.jl:100-101 (xms_el, cps_el), Mesh.jl:311-319 (table lookup by unique element).
 // ---------------------------------------------------------------------------------------------------------
 MAF_HD void phase_gather(int tid, int nt, const Config& cfg, const Tables& T, int64_t el, const double* xms,
-                         const double* cps, double* sm) {
-  int32_t* si = reinterpret_cast<int32_t*>(sm + cfg.o_int);
+                         const double* cps, double* fr /* front block of this element */) {
+  int32_t* si = reinterpret_cast<int32_t*>(fr + cfg.o_int);
   const int64_t np = T.numnp;
   for (int k = tid; k < 9 * 13; k += nt) {
     const int a = k % 9, q = k / 9;
     const int64_t node = T.IX[9 * el + a];
     if (q < 3) {
-      sm[cfg.o_x + 9 * q + a] = xms[node + np * q];
+      fr[cfg.o_x + 9 * q + a] = xms[node + np * q];
     } else if (q < 11) {
       // q-3 enumerates (field, comp): v0 v1 v2 m0 m1 m2 l p
       const int u = q - 3;
@@ -174,7 +175,7 @@ MAF_HD void phase_gather(int tid, int nt, const Config& cfg, const Tables& T, in
       const int dof = cfg.fdof[f][i];
       const double val = dof >= 0 ? cps[node + np * dof] : 0.0;  // absent dofs read as zero (GeoDynStress.jl:196-202)
       const int base = f == F_V ? cfg.o_cv : (f == F_M ? cfg.o_cm : (f == F_L ? cfg.o_cl : cfg.o_cp));
-      sm[base + 9 * i + a] = val;
+      fr[base + 9 * i + a] = val;
     } else if (q == 11) {
       si[I_NODE + a] = (int32_t)node;
       si[I_MASK + a] = T.nodemask[node];
@@ -186,8 +187,8 @@ MAF_HD void phase_gather(int tid, int nt, const Config& cfg, const Tables& T, in
   //   slot(a, I; b, J) = base + cprel[8 b + J] + po[(9 a + b) * 8 + J] + rank(I | a, J)
   // base = a column pointer that bounds the element's columns from below, cprel = column pointer of (b, J)
   // relative to it (int32; SLOT_NONE for a Dirichlet column), po = the pairoff row of the node pair (a, b).
-  int32_t* cprel = reinterpret_cast<int32_t*>(sm + cfg.o_slot);
-  unsigned long long* po = reinterpret_cast<unsigned long long*>(sm + cfg.o_po);
+  int32_t* cprel = reinterpret_cast<int32_t*>(fr + cfg.o_slot);
+  unsigned long long* po = reinterpret_cast<unsigned long long*>(fr + cfg.o_po);
   const int64_t base = T.colptr[T.eq0[T.IX[9 * el]]];
   for (int k = tid; k < 72 + 81; k += nt) {
     if (k < 72) {
@@ -202,21 +203,16 @@ MAF_HD void phase_gather(int tid, int nt, const Config& cfg, const Tables& T, in
       po[k - 72] = *reinterpret_cast<const unsigned long long*>(T.pairoff + (int64_t)T.elpair[81 * el + (k - 72)] * 8);
     }
   }
-  if (tid == 0) *reinterpret_cast<int64_t*>(sm + cfg.o_base) = base;
+  if (tid == 0) *reinterpret_cast<int64_t*>(fr + cfg.o_base) = base;
   // basis block of this element: Phi[gp][c][a2][4] | FG[gp][18] | w[9]   (contiguous, BASIS_DOUBLES)
   const int e1 = (int)(el % T.num1el), e2 = (int)(el / T.num1el);
   if (T.utab) {   // precomputed per unique element (same products, formed once on the host): straight copy
     const dbl2* src = reinterpret_cast<const dbl2*>(T.utab + (size_t)BASIS_DOUBLES * (T.uel1[e1] + (size_t)T.nuel1 * T.uel2[e2]));
-    dbl2* dst = reinterpret_cast<dbl2*>(sm + cfg.o_phi);
+    dbl2* dst = reinterpret_cast<dbl2*>(fr + cfg.o_phi);
     for (int k = tid; k < BASIS_DOUBLES / 2; k += nt) dst[k] = src[k];
   } else {
-    build_basis_block(tid, nt, T.line1 + 30 * T.uel1[e1], T.line2 + 30 * T.uel2[e2], sm + cfg.o_phi);
-  }
-  // the closed-form columns of the Gauss-point tangent touch only a few rows: start from zero
-  {
-    dbl2* Az = reinterpret_cast<dbl2*>(sm + cfg.o_A);
-    const dbl2 z = {0.0, 0.0};
-    for (int k = tid; k < 9 * cfg.asize / 2; k += nt) Az[k] = z;
+    build_basis_block(tid, nt, T.line1 + 30 * T.uel1[e1], T.line2 + 30 * T.uel2[e2],
+                      T.tdb + 81 * ((int64_t)T.uel1[e1] + (int64_t)T.nuel1 * T.uel2[e2]), fr + cfg.o_phi);
   }
 }
 
@@ -242,7 +238,13 @@ MAF_HD void prefetch_next(int lane, const Config& cfg, const Tables& T, int64_t 
 // ---------------------------------------------------------------------------------------------------------
 // Phase 1: interpolate the Gauss-point inputs E[gp][.] (GeoDynStress.jl:111-115, 135-143).
 // ---------------------------------------------------------------------------------------------------------
-MAF_HD void phase_interp(int tid, int nt, const Config& cfg, double* sm) {
+MAF_HD void phase_interp(int tid, int nt, const Config& cfg, const double* fr, double* sm) {
+  // the closed-form columns of the Gauss-point tangent touch only a few rows: start from zero
+  {
+    dbl2* Az = reinterpret_cast<dbl2*>(sm + cfg.o_A);
+    const dbl2 z = {0.0, 0.0};
+    for (int k = tid; k < 9 * cfg.asize / 2; k += nt) Az[k] = z;
+  }
   for (int k = tid; k < 9 * 35; k += nt) {
     const int gp = k / 35, q = k % 35;
     int src, ch;
@@ -254,10 +256,10 @@ MAF_HD void phase_interp(int tid, int nt, const Config& cfg, double* sm) {
     else if (q < 33) { ch = CH_N; src = cfg.o_cm + 9 * (q - 30); }
     else if (q == 33) { ch = CH_N; src = cfg.o_cl; }
     else { ch = CH_N; src = cfg.o_cp; }
-    const double* ph = sm + cfg.o_phi + PHI_GP * gp + PHI_C * ch;
+    const double* ph = fr + cfg.o_phi + PHI_GP * gp + PHI_C * ch;
     double s = 0.0;
 #pragma unroll
-    for (int a = 0; a < 9; ++a) s += sm[src + a] * ph[4 * (a / 3) + (a % 3)];
+    for (int a = 0; a < 9; ++a) s += fr[src + a] * ph[4 * (a / 3) + (a % 3)];
     sm[cfg.o_E + E_STRIDE * gp + q] = s;
   }
 }
@@ -343,11 +345,11 @@ MAF_HD void load_E(const double* E, double a[2][3], double c[3][3], double dv[2]
 //                       (the residual is affine in cps at fixed x)
 // ---------------------------------------------------------------------------------------------------------
 template <int MOTION>
-MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, double* sm) {
+MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const double* fr, double* sm) {
   const int gp = it.gp;
   const double* E = sm + cfg.o_E + E_STRIDE * gp;
   double* Agp = sm + cfg.o_A + (size_t)cfg.asize * gp;
-  const double w = sm[cfg.o_w + gp];
+  const double w = fr[cfg.o_w + gp];
   double a[2][3], c[3][3], dv[2][3], v[3], dm[2][3], vm[3], lam, pm;
   load_E(E, a, c, dv, v, dm, vm, lam, pm);
   const int mf = cfg.mesh_field;
@@ -483,21 +485,20 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, double
 }
 
 template <int MOTION>
-MAF_HD void phase_gauss(int tid, const Config& cfg, double dt, double* sm) {
+MAF_HD void phase_gauss(int tid, const Config& cfg, double dt, const double* fr, double* sm) {
   for (int r = 0; r < cfg.item_rounds; ++r) {
     const int id = cfg.item_slot[r * cfg.nthreads + tid];
-    if (id >= 0) phase_gauss_item<MOTION>(cfg, cfg.items[id], dt, sm);
+    if (id >= 0) phase_gauss_item<MOTION>(cfg, cfg.items[id], dt, fr, sm);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Phase 3a: element residual r_el and its scatter (FiniteElement.jl:103, 129-131).
 // ---------------------------------------------------------------------------------------------------------
-MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const Tables& T, int64_t el, double* sm, double* r_gl,
+MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const double* fr, const double* sm, double* r_gl,
                            double* r_stage /* deterministic path: 72 staged rows of this element, or NULL */) {
-  const int32_t* si = reinterpret_cast<const int32_t*>(sm + cfg.o_int);
-  const int e1 = (int)(el % T.num1el), e2 = (int)(el / T.num1el);
-  const double* tdb = T.tdb + 81 * ((int64_t)T.uel1[e1] + (int64_t)T.nuel1 * T.uel2[e2]);
+  const int32_t* si = reinterpret_cast<const int32_t*>(fr + cfg.o_int);
+  const double* tdb = fr + cfg.o_tdb;
   for (int k = tid; k < 72; k += nt) {
     const int a = k % 9, u = k / 9;
     const int f = u < 3 ? F_V : (u < 6 ? F_M : (u == 6 ? F_L : F_P));
@@ -511,7 +512,7 @@ MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const Tables& T, 
     double s = 0.0;
     for (int gp = 0; gp < 9; ++gp) {
       const double* Sg = sm + cfg.o_S + S_STRIDE * gp;
-      const double* ph = sm + cfg.o_phi + PHI_GP * gp + phi_a(a);
+      const double* ph = fr + cfg.o_phi + PHI_GP * gp + phi_a(a);
       double t;
       if (f == F_V || f == F_M) {
         const int sb = f == F_V ? S_V : S_M;
@@ -521,10 +522,10 @@ MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const Tables& T, 
       } else {
         t = Sg[f == F_L ? S_L : S_P] * ph[0];
       }
-      s += sm[cfg.o_w + gp] * t;
+      s += fr[cfg.o_w + gp] * t;
     }
     if (f == F_L || (f == F_P)) {  // Dohrmann-Bochev projection of the nodal lambda / pm (FiniteElement.jl:323-327)
-      const double* nod = sm + (f == F_L ? cfg.o_cl : cfg.o_cp);
+      const double* nod = fr + (f == F_L ? cfg.o_cl : cfg.o_cp);
       double t = 0.0;
 #pragma unroll
       for (int b = 0; b < 9; ++b) t += tdb[9 * a + b] * nod[b];
@@ -667,18 +668,18 @@ struct KSink {
   int nij;
 };
 
-MAF_HD void phase_tangent_task(const Config& cfg, const Tables& T, int64_t el, int task_id, const double* sm,
+MAF_HD void phase_tangent_task(const Config& cfg, int task_id, const double* fr, const double* sm,
                                const KSink& sink) {
   const Task tk = cfg.tasks[task_id];
   const Block bk = cfg.blocks[tk.blk];
   const int f = bk.f, g = bk.g, i = tk.i, j = tk.j, a2 = tk.a2;
   const double* A0 = sm + cfg.o_A + a_index(cfg, f, i, bk.c0, g, j, bk.d0);
-  const double* Phi = sm + cfg.o_phi;
+  const double* Phi = fr + cfg.o_phi;
   const int ald = cfg.ald[f];
   // offset from the (j, N1) entry of a row to its b-direction columns
   const int boff = bk.mesh ? cfg.bcol[f] - (cfg.coloff[f][g] + j * cfg.cnc[f][g]) : 0;
   const double* G = sm + cfg.o_G;
-  const double* FG = sm + cfg.o_FG;
+  const double* FG = fr + cfg.o_FG;
   double acc[3][9];
   switch (bk.kind) {
     case 0: block_accumulate<1, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
@@ -690,10 +691,9 @@ MAF_HD void phase_tangent_task(const Config& cfg, const Tables& T, int64_t el, i
     case 6: block_accumulate_mesh<5>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a2, i, j, bk.qterm, acc); break;
     default: block_accumulate_mesh<6>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a2, i, j, bk.qterm, acc); break;
   }
-  const int32_t* si = reinterpret_cast<const int32_t*>(sm + cfg.o_int);
+  const int32_t* si = reinterpret_cast<const int32_t*>(fr + cfg.o_int);
   if (bk.db) {  // Dohrmann-Bochev stabilisation matrix (state independent), FiniteElement.jl:323-327
-    const int e1 = (int)(el % T.num1el), e2 = (int)(el / T.num1el);
-    const double* tdb = T.tdb + 81 * ((int64_t)T.uel1[e1] + (int64_t)T.nuel1 * T.uel2[e2]);
+    const double* tdb = fr + cfg.o_tdb;
 #pragma unroll
     for (int a1 = 0; a1 < 3; ++a1)
 #pragma unroll
@@ -710,31 +710,30 @@ MAF_HD void phase_tangent_task(const Config& cfg, const Tables& T, int64_t el, i
   // atomics path: K_gl[LM[i], LM[j]] += K_el[i, j] for active rows and columns (FiniteElement.jl:129-136)
   const int I = cfg.fdof[f][i], J = cfg.fdof[g][j];
   const unsigned rmask = cfg.rowmask[J] & ((1u << I) - 1u);
-  const int32_t* cprel = reinterpret_cast<const int32_t*>(sm + cfg.o_slot);
-  const uint8_t* po8 = reinterpret_cast<const uint8_t*>(sm + cfg.o_po);
-  double* nzb = sink.nzval + *reinterpret_cast<const int64_t*>(sm + cfg.o_base);
-  double* dst[3];
-  bool act[3];
+  const int32_t* cprel = reinterpret_cast<const int32_t*>(fr + cfg.o_slot) + J;
+  const uint8_t* po8 = reinterpret_cast<const uint8_t*>(fr + cfg.o_po) + 72 * 3 * a2 + J;   // row of node (0, a2)
+  double* nzb = sink.nzval + *reinterpret_cast<const int64_t*>(fr + cfg.o_base);
+  int off[3];
 #pragma unroll
   for (int a1 = 0; a1 < 3; ++a1) {
     const unsigned m = (unsigned)si[I_MASK + a1 + 3 * a2];
-    act[a1] = (m >> I) & 1u;            // rows of inactive dofs are discarded
-    dst[a1] = nzb + popc8(m & rmask);
+    // rows of inactive dofs are discarded: an offset that can never be reached marks them
+    off[a1] = ((m >> I) & 1u) ? popc8(m & rmask) : SLOT_NONE;
   }
 #pragma unroll
   for (int b = 0; b < 9; ++b) {
-    const int32_t rel = cprel[8 * b + J];
+    const int rel = cprel[8 * b];
     if (rel == SLOT_NONE) continue;
 #pragma unroll
     for (int a1 = 0; a1 < 3; ++a1)
-      if (act[a1]) atomic_add(dst[a1] + rel + po8[(9 * (a1 + 3 * a2) + b) * 8 + J], acc[a1][b]);
+      if (off[a1] != SLOT_NONE) atomic_add(nzb + (off[a1] + rel + (int)po8[72 * a1 + 8 * b]), acc[a1][b]);
   }
 }
 
-MAF_HD void phase_tangent(int tid, const Config& cfg, const Tables& T, int64_t el, const double* sm, const KSink& sink) {
+MAF_HD void phase_tangent(int tid, const Config& cfg, const double* fr, const double* sm, const KSink& sink) {
   for (int r = 0; r < cfg.task_rounds; ++r) {
     const int id = cfg.task_slot[r * cfg.nthreads + tid];
-    if (id >= 0) phase_tangent_task(cfg, T, el, id, sm, sink);
+    if (id >= 0) phase_tangent_task(cfg, id, fr, sm, sink);
   }
 }
 

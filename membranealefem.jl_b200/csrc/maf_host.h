@@ -103,6 +103,7 @@ inline void build_host_model(HostModel& M, const maf_mesh_desc* d, const maf_par
     for (int u2 = 0; u2 < M.nuel2; ++u2)
       for (int u1 = 0; u1 < M.nuel1; ++u1)
         build_basis_block(0, 1, M.line1.data() + 30 * u1, M.line2.data() + 30 * u2,
+                          M.tdb.data() + (size_t)81 * (u1 + (size_t)M.nuel1 * u2),
                           M.utab.data() + (size_t)BASIS_DOUBLES * (u1 + (size_t)M.nuel1 * u2));
   }
 

@@ -17,19 +17,31 @@ static void run_area(const HostModel& M, const Tables& T, const double* xms, con
                      double* nzval, double* kel, double* rel, const GatherHost* GH, int64_t e0, int64_t e1) {
   const Config& cfg = M.cfg;
   const int nt = cfg.nthreads;
-  std::vector<double> sm(cfg.smem_doubles);
+  std::vector<double> smem_all(cfg.smem_doubles);
   std::vector<int32_t> order;
   build_element_order(M.num1el, e0, e1, order);
-  for (size_t k = 0; k < order.size(); ++k) {
+  const int nfront = cfg.front_doubles;
+  double* sm = smem_all.data() + 2 * nfront;
+  // same software pipeline as the kernel: the "last warp" (32 lanes) gathers the next element into the other buffer
+  std::fill(smem_all.begin(), smem_all.end(), std::nan(""));  // any read of an unwritten slot poisons the result
+  if (!order.empty())
+    for (int t = 0; t < nt; ++t) phase_gather(t, nt, cfg, T, order[0], xms, cps, smem_all.data());
+  int cur = 0;
+  for (size_t k = 0; k < order.size(); ++k, cur ^= 1) {
     const int64_t el = order[k];
-    std::fill(sm.begin(), sm.end(), std::nan(""));  // any read of an unwritten slot poisons the result
-    for (int t = 0; t < nt; ++t) phase_gather(t, nt, cfg, T, el, xms, cps, sm.data());
-    for (int t = 0; t < nt; ++t) phase_interp(t, nt, cfg, sm.data());
-    for (int t = 0; t < nt; ++t) phase_gauss<MOTION>(t, cfg, dt, sm.data());
+    const double* fr = smem_all.data() + cur * nfront;
+    std::fill(sm, smem_all.data() + smem_all.size(), std::nan(""));
+    for (int t = 0; t < nt; ++t) phase_interp(t, nt, cfg, fr, sm);
+    for (int t = 0; t < nt; ++t) phase_gauss<MOTION>(t, cfg, dt, fr, sm);
+    if (k + 1 < order.size()) {
+      double* nf = smem_all.data() + (cur ^ 1) * nfront;
+      std::fill(nf, nf + nfront, std::nan(""));
+      for (int l = 0; l < 32; ++l) phase_gather(l, 32, cfg, T, order[k + 1], xms, cps, nf);
+    }
     KSink sink{nzval, nullptr, nullptr, 0};
     if (kel) sink = KSink{nullptr, kel + (size_t)81 * GH->nij * (el - e0), GH->task_ij.data(), GH->nij};
-    for (int t = 0; t < nt; ++t) phase_residual(t, nt, cfg, T, el, sm.data(), r, rel ? rel + 72 * (el - e0) : nullptr);
-    for (int t = 0; t < nt; ++t) phase_tangent(t, cfg, T, el, sm.data(), sink);
+    for (int t = 0; t < nt; ++t) phase_residual(t, nt, cfg, fr, sm, r, rel ? rel + 72 * (el - e0) : nullptr);
+    for (int t = 0; t < nt; ++t) phase_tangent(t, cfg, fr, sm, sink);
   }
 }
 
