@@ -186,6 +186,12 @@ struct maf_handle {
   // what that range touches: nodes [node_lo, node_hi), equations [eq_lo, eq_hi), nnz slots [slot_lo, slot_hi)
   int64_t node_lo = 0, node_hi = 0, eq_lo = 0, eq_hi = 0, slot_lo = 0, slot_hi = 0;
   bool timed_valid = false;
+  // pipelined host path (maf_assemble): strips of element rows whose finished nzval/r ranges are copied to the
+  // host on a second stream while the next strip is being assembled
+  struct Strip { int64_t e0, e1, eq_lo, slot_lo; int32_t* d_order; };
+  std::vector<Strip> strips;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> strip_ev;
   int64_t launches = 0;
   float ms[7] = {0, 0, 0, 0, 0, 0, 0};
 };
@@ -252,6 +258,34 @@ static void compute_ranges(maf_handle* h) {
   if (!order.empty()) CU(cudaMemcpy(h->d_order, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
 }
 
+static void ensure_strips(maf_handle* h, int nstrips) {
+  if (!h->strips.empty()) return;
+  const HostModel& M = h->M;
+  CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int q = 0; q < nstrips; ++q) {
+    const int64_t r0 = ((int64_t)q * M.num2el) / nstrips, r1 = ((int64_t)(q + 1) * M.num2el) / nstrips;
+    if (r1 <= r0) continue;
+    maf_handle::Strip st;
+    st.e0 = r0 * M.num1el;
+    st.e1 = r1 * M.num1el;
+    int64_t lo = M.numnp;
+    for (int64_t k = 9 * st.e0; k < 9 * st.e1; ++k) lo = std::min<int64_t>(lo, M.IX0[k]);
+    int64_t eq_lo = M.nmdf;
+    for (int64_t k = lo * M.ndf; k < M.numnp * M.ndf; ++k)
+      if (M.ID0[k] >= 0) { eq_lo = M.ID0[k]; break; }
+    st.eq_lo = eq_lo;
+    st.slot_lo = M.sym.colptr[eq_lo];
+    std::vector<int32_t> order;
+    build_element_order(M.num1el, st.e0, st.e1, order);
+    CU(cudaMalloc(&st.d_order, order.size() * sizeof(int32_t)));
+    CU(cudaMemcpy(st.d_order, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->strips.push_back(st);
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->strip_ev.push_back(e);
+  }
+}
+
 static void ensure_gather(maf_handle* h) {
   if (h->gather_ready) return;
   const HostModel& M = h->M;
@@ -290,6 +324,30 @@ static void ensure_stage(maf_handle* h) {
   CU(cudaMalloc(&h->d_kel, ne * 81 * h->nij * sizeof(double)));
   CU(cudaMalloc(&h->d_rel, ne * 72 * sizeof(double)));
   h->kel_elems = ne;
+}
+
+// area + boundary kernels of the elements [e0, e1) on the atomics path (outputs must have been zeroed)
+static void launch_atomic_range(maf_handle* h, const double* d_xms, const double* d_cps, double time, double dt,
+                                double bend_tm, double* d_r, double* d_nz, cudaStream_t s, int64_t e0, int64_t e1,
+                                const int32_t* d_order) {
+  const HostModel& M = h->M;
+  area_fn kern = area_kernel_of(M.motion);
+  const int64_t ne = e1 - e0;
+  if (ne <= 0) return;
+  const int grid = (int)std::min<int64_t>(ne, (int64_t)h->grid);
+  StageSink st{nullptr, nullptr, nullptr, 0};
+  kern<<<grid, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, d_order, e0, e1);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  for (int bc = 0; bc < M.n_neu; ++bc) {
+    const int n = M.b_offs[bc + 1] - M.b_offs[bc];
+    if (n == 0) continue;
+    const double fval = neumann_value(M.b_type[bc], M.b_val[bc], time, bend_tm);
+    const int gb = std::min((n + 3) / 4, h->sm_count * 8);
+    boundary_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, h->BT, bc, fval, dt, d_xms, d_r, d_nz, -1, 1, e0, e1);
+    CU(cudaGetLastError());
+    h->launches += 1;
+  }
 }
 
 static void do_assemble_device(maf_handle* h, const double* d_xms, const double* d_cps, double time, double dt,
@@ -481,6 +539,9 @@ int maf_destroy(maf_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
   if (h->d_order) cudaFree(h->d_order);
+  for (auto& st : h->strips) cudaFree(st.d_order);
+  for (auto& e : h->strip_ev) cudaEventDestroy(e);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->d_kel) cudaFree(h->d_kel);
   if (h->d_rel) cudaFree(h->d_rel);
   if (h->h_pin_in) cudaFreeHost(h->h_pin_in);
@@ -508,33 +569,94 @@ int maf_pattern(maf_handle* h, int64_t* colptr, int64_t* rowval) {
   MAF_API_END(h)
 }
 
+// is this host pointer page-locked (cudaMallocHost / cudaHostRegister)? then it can be copied from directly
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 int maf_assemble(maf_handle* h, const double* xms, const double* cps, double time, double dt, double bend_tm,
                  int scatter_mode, double* r, double* nzval, double* rnorm2) {
   MAF_API_BEGIN(h)
   if (!xms || !cps || !r || !nzval) throw std::runtime_error("null buffer");
+  if (scatter_mode != MAF_SCATTER_ATOMIC && scatter_mode != MAF_SCATTER_DETERMINISTIC)
+    throw std::runtime_error("unknown scatter mode");
   const HostModel& M = h->M;
   cudaStream_t s = h->stream;
   const size_t bx = sizeof(double) * 3 * (size_t)M.numnp, bc = sizeof(double) * (size_t)M.ndf * M.numnp;
   const size_t br = sizeof(double) * (size_t)M.nmdf, bk = sizeof(double) * (size_t)M.sym.nnz;
-  // pinned staging keeps the copies asynchronous and at full PCIe rate whatever memory the caller owns
-  if (h->pin_in_bytes < bx + bc) {
-    if (h->h_pin_in) cudaFreeHost(h->h_pin_in);
-    CU(cudaMallocHost(&h->h_pin_in, bx + bc));
-    h->pin_in_bytes = bx + bc;
-  }
   CU(cudaEventRecord(h->ev[0], s));
-  std::memcpy(h->h_pin_in, xms, bx);
-  std::memcpy((char*)h->h_pin_in + bx, cps, bc);
-  CU(cudaMemcpyAsync(h->d_xms, h->h_pin_in, bx, cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(h->d_cps, (char*)h->h_pin_in + bx, bc, cudaMemcpyHostToDevice, s));
-  do_assemble_device(h, h->d_xms, h->d_cps, time, dt, bend_tm, scatter_mode, h->d_r, h->d_nz,
-                     rnorm2 ? h->d_rn : nullptr, s, true);
-  // results straight into the caller's buffers (pageable destinations are staged by the driver)
-  CU(cudaMemcpyAsync(r, h->d_r, br, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(nzval, h->d_nz, bk, cudaMemcpyDeviceToHost, s));
-  if (rnorm2) CU(cudaMemcpyAsync(rnorm2, h->d_rn, sizeof(double), cudaMemcpyDeviceToHost, s));
-  CU(cudaEventRecord(h->ev[5], s));
-  CU(cudaStreamSynchronize(s));
+  // inputs: page-locked caller memory is copied from directly, anything else through a pinned staging buffer
+  // (keeps the copy asynchronous and at full PCIe rate)
+  const double *hx = xms, *hc = cps;
+  if (!is_pinned(xms) || !is_pinned(cps)) {
+    if (h->pin_in_bytes < bx + bc) {
+      if (h->h_pin_in) cudaFreeHost(h->h_pin_in);
+      CU(cudaMallocHost(&h->h_pin_in, bx + bc));
+      h->pin_in_bytes = bx + bc;
+    }
+    std::memcpy(h->h_pin_in, xms, bx);
+    std::memcpy((char*)h->h_pin_in + bx, cps, bc);
+    hx = h->h_pin_in;
+    hc = (const double*)((char*)h->h_pin_in + bx);
+  }
+  CU(cudaMemcpyAsync(h->d_xms, hx, bx, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(h->d_cps, hc, bc, cudaMemcpyHostToDevice, s));
+  const bool full = h->e0 == 0 && h->e1 == M.numel;
+  const bool pipelined = scatter_mode == MAF_SCATTER_ATOMIC && full && M.numel >= 32768 && M.num2el >= 16;
+  if (!pipelined) {
+    do_assemble_device(h, h->d_xms, h->d_cps, time, dt, bend_tm, scatter_mode, h->d_r, h->d_nz,
+                       rnorm2 ? h->d_rn : nullptr, s, true);
+    // results straight into the caller's buffers (pageable destinations are staged by the driver)
+    CU(cudaMemcpyAsync(r, h->d_r, br, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(nzval, h->d_nz, bk, cudaMemcpyDeviceToHost, s));
+    if (rnorm2) CU(cudaMemcpyAsync(rnorm2, h->d_rn, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(h->ev[5], s));
+    CU(cudaStreamSynchronize(s));
+  } else {
+    // strips of element rows: everything below the first slot a later strip touches is final once a strip is
+    // done, so its device-to-host copy (the dominant cost: nnz * 8 bytes over PCIe) overlaps the next strips
+    ensure_strips(h, 8);
+    if (!(dt == dt) || !(time == time)) throw std::runtime_error("time / dt is NaN");
+    h->timed_valid = false;
+    CU(cudaEventRecord(h->ev[1], s));
+    CU(cudaMemsetAsync(h->d_r, 0, br, s));
+    CU(cudaMemsetAsync(h->d_nz, 0, bk, s));
+    CU(cudaEventRecord(h->ev[6], s));
+    const size_t ns = h->strips.size();
+    for (size_t q = 0; q < ns; ++q) {
+      const maf_handle::Strip& st = h->strips[q];
+      launch_atomic_range(h, h->d_xms, h->d_cps, time, dt, bend_tm, h->d_r, h->d_nz, s, st.e0, st.e1, st.d_order);
+      CU(cudaEventRecord(h->strip_ev[q], s));
+    }
+    CU(cudaEventRecord(h->ev[2], s));
+    CU(cudaEventRecord(h->ev[3], s));
+    CU(cudaEventRecord(h->ev[4], s));
+    h->timed_valid = true;
+    for (size_t q = 0; q < ns; ++q) {
+      const int64_t s_lo = q == 0 ? 0 : h->strips[q].slot_lo, s_hi = q + 1 < ns ? h->strips[q + 1].slot_lo : M.sym.nnz;
+      const int64_t r_lo = q == 0 ? 0 : h->strips[q].eq_lo, r_hi = q + 1 < ns ? h->strips[q + 1].eq_lo : M.nmdf;
+      CU(cudaStreamWaitEvent(h->copy_stream, h->strip_ev[q], 0));
+      if (s_hi > s_lo)
+        CU(cudaMemcpyAsync(nzval + s_lo, h->d_nz + s_lo, sizeof(double) * (size_t)(s_hi - s_lo),
+                           cudaMemcpyDeviceToHost, h->copy_stream));
+      if (r_hi > r_lo)
+        CU(cudaMemcpyAsync(r + r_lo, h->d_r + r_lo, sizeof(double) * (size_t)(r_hi - r_lo), cudaMemcpyDeviceToHost,
+                           h->copy_stream));
+    }
+    if (rnorm2) {
+      rnorm2_partial<<<256, 256, 0, s>>>(h->d_r, M.nmdf, h->d_part);
+      rnorm2_final<<<1, 256, 0, s>>>(h->d_part, 256, h->d_rn);
+      CU(cudaGetLastError());
+      h->launches += 2;
+      // (a copy into pageable host memory blocks the host until the stream drains: issue it last)
+      CU(cudaMemcpyAsync(rnorm2, h->d_rn, sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(h->copy_stream));
+    CU(cudaEventRecord(h->ev[5], s));
+    CU(cudaStreamSynchronize(s));
+  }
   CU(cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]));
   CU(cudaEventElapsedTime(&h->ms[4], h->ev[4], h->ev[5]));
   CU(cudaEventElapsedTime(&h->ms[5], h->ev[0], h->ev[5]));
