@@ -150,6 +150,11 @@ int maf_range_info(maf_handle* h, int64_t* out8);
 /* Measured FP64 FMA throughput of the device (TFLOP/s): the denominator of the FP64 roofline fraction. */
 int maf_fp64_peak(int device, double* tflops);
 
+/* Profiling hook. In builds with -DMAF_PHASE_TIMING: cycles per (warp, phase) of the element kernel summed over
+ * all CTAs since the previous call, out[8 * warp + phase], phases = wait, interpolate, wait, gauss, wait,
+ * gather-next, residual+tangent, unused; returns 0. Regular builds return 1 and leave `out` untouched. */
+int maf_debug_phase_cycles(unsigned long long* out, int n);
+
 #ifdef __cplusplus
 }
 #endif

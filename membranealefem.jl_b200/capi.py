@@ -43,7 +43,8 @@ _lib = None
 
 EXPORTS = ["maf_create", "maf_destroy", "maf_last_error", "maf_nnz", "maf_pattern", "maf_assemble",
            "maf_assemble_device", "maf_device_buffers", "maf_stream", "maf_sync", "maf_timings", "maf_launch_count",
-           "maf_kernel_info", "maf_set_element_range", "maf_range_info", "maf_fp64_peak"]
+           "maf_kernel_info", "maf_set_element_range", "maf_range_info", "maf_fp64_peak",
+           "maf_debug_phase_cycles"]
 
 
 def load_library(path=None):

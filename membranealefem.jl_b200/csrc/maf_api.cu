@@ -23,7 +23,6 @@
 
 using namespace maf;
 
-#define MAF_NT 128  // threads per CTA of the area kernel (one element per CTA iteration)
 #ifndef MAF_MIN_CTAS
 #define MAF_MIN_CTAS 3  // resident CTAs per SM the register allocation is capped for
 #endif
@@ -36,9 +35,25 @@ static_assert(sizeof(Config) <= 4000, "Config must fit the kernel parameter spac
 struct StageSink {      // deterministic path staging buffers (NULL = atomics path)
   double* kel;          // numel_local x 81 x nij
   double* rel;          // numel_local x 72
-  const int16_t* task_ij;  // per task: column of the (I,J) class in the staging row
   int nij;
 };
+
+#ifdef MAF_PHASE_TIMING   // profiling build only: cycles per warp and phase, summed over all CTAs
+__device__ unsigned long long g_phase_cycles[MAF_NT / 32][8];
+__device__ __forceinline__ long long maf_clock() {   // not to be moved across barriers or memory operations
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+#define MAF_TICK(k)                                                   \
+  {                                                                   \
+    const long long t_now = maf_clock();                              \
+    t_acc[k] += t_now - t_last;                                       \
+    t_last = t_now;                                                   \
+  }
+#else
+#define MAF_TICK(k)
+#endif
 
 template <int MOTION>
 __global__ void __launch_bounds__(MAF_NT, MAF_MIN_CTAS)
@@ -49,37 +64,74 @@ area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __
   const int tid = threadIdx.x;
   const int64_t ne = e1 - e0;
   const int nfront = cfg.front_doubles;
-  double* sm = smem_all + 2 * nfront;   // back block: E, S, G, A
-  // software pipeline over the elements of this CTA: while element k is contracted (the longest phase), the last
-  // warp first gathers element k + gridDim.x into the other front buffer, so the dependent global loads of the
-  // gather (IX -> ID -> colptr, elpair -> pairoff) are off the critical path of the CTA. (Gathering during the
-  // shorter interpolate/Gauss window with named barriers was measured slower: profiles/r1_notes.md.)
-  if ((int64_t)blockIdx.x < ne) phase_gather(tid, MAF_NT, cfg, T, order[blockIdx.x], xms, cps, smem_all);
+  int32_t* ids0 = reinterpret_cast<int32_t*>(smem_all + 2 * nfront);
+  double* sm = smem_all + 2 * nfront + 2 * MAF_IDS_DOUBLES;   // back block: E, S, G, A
+  // Software pipeline over the elements of this CTA (k, k + G, k + 2G, ...; G = gridDim.x). At the top of the
+  // iteration of element k every thread issues asynchronous global -> shared copies (cp.async): the data of
+  // element k + G into the other front buffer, addressed through the node / pair ids that were copied during the
+  // previous iteration, and the ids of element k + 2G. They are awaited at the end of the iteration, a whole
+  // element later: the gather costs neither registers nor exposed latency. (One warp gathering item by item took
+  // as long as the contraction phase; all threads with batched loads still lost 10-20 % of their time waiting:
+  // profiles/r1_notes.md.)
+  const int64_t G = gridDim.x;
+  // elements of this iteration / the next / the one after; the order is read one iteration before it is needed
+  int32_t el_cur = 0, el_nxt = 0, el_ids = 0;
+  gather_init(tid, cfg, smem_all);
+  gather_init(tid, cfg, smem_all + nfront);
+  if ((int64_t)blockIdx.x < ne) {
+    el_cur = order[blockIdx.x];
+    if (blockIdx.x + G < ne) el_nxt = order[blockIdx.x + G];
+    if (blockIdx.x + 2 * G < ne) el_ids = order[blockIdx.x + 2 * G];
+    gather_ids_async(tid, T, el_cur, ids0);
+    async_wait_all();
+    __syncthreads();
+    gather_data_async(tid, cfg, T, ids0, xms, cps, smem_all);
+    if (blockIdx.x + G < ne) gather_ids_async(tid, T, el_nxt, ids0 + MAF_IDS_INTS);
+    async_wait_all();
+  }
   int cur = 0;
-  for (int64_t k = blockIdx.x; k < ne; k += gridDim.x, cur ^= 1) {
-    const int64_t el = order[k];
+#ifdef MAF_PHASE_TIMING
+  long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_last = maf_clock();
+#endif
+  for (int64_t k = blockIdx.x; k < ne; k += G, cur ^= 1) {
+    const int64_t el = el_cur;
     const double* fr = smem_all + cur * nfront;
-    __syncthreads();   // front buffer `cur` complete; back block and front buffer `cur ^ 1` free
-    phase_interp(tid, MAF_NT, cfg, fr, sm);
-    __syncthreads();
-    phase_gauss<MOTION>(tid, cfg, dt, fr, sm);
-    __syncthreads();
-    const int64_t kn = k + gridDim.x;
-    if (tid >= MAF_NT - 32 && kn < ne) {
-      phase_gather(tid & 31, 32, cfg, T, order[kn], xms, cps, smem_all + (cur ^ 1) * nfront);
-      if (kn + gridDim.x < ne) prefetch_next(tid & 31, cfg, T, order[kn + gridDim.x], xms, cps);
+    __syncthreads();   // front buffer `cur` and the ids of the next element complete; everything else is free
+    MAF_TICK(0)
+    const int64_t kn = k + G;
+    if (kn < ne) {
+      gather_data_async(tid, cfg, T, ids0 + (cur ^ 1) * MAF_IDS_INTS, xms, cps, smem_all + (cur ^ 1) * nfront);
+      if (kn + G < ne) gather_ids_async(tid, T, el_ids, ids0 + cur * MAF_IDS_INTS);
+      el_cur = el_nxt;
+      el_nxt = el_ids;
+      if (kn + 2 * G < ne) el_ids = order[kn + 2 * G];
     }
+    phase_interp(tid, MAF_NT, cfg, fr, sm);
+    MAF_TICK(1)
+    __syncthreads();
+    MAF_TICK(2)
+    phase_gauss<MOTION>(tid, cfg, dt, fr, sm);
+    MAF_TICK(3)
+    __syncthreads();
+    MAF_TICK(4)
+    MAF_TICK(5)
     if (st.kel == nullptr) {
       phase_residual(tid, MAF_NT, cfg, fr, sm, r_gl, nullptr);
-      KSink sink{nzval, nullptr, nullptr, 0};
+      KSink sink{nzval, nullptr, 0};
       phase_tangent(tid, cfg, fr, sm, sink);
     } else {
       const int64_t le = el - e0;
       phase_residual(tid, MAF_NT, cfg, fr, sm, nullptr, st.rel + 72 * le);
-      KSink sink{nullptr, st.kel + (size_t)81 * st.nij * le, st.task_ij, st.nij};
+      KSink sink{nullptr, st.kel + (size_t)81 * st.nij * le, st.nij};
       phase_tangent(tid, cfg, fr, sm, sink);
     }
+    async_wait_all();
+    MAF_TICK(6)
   }
+#ifdef MAF_PHASE_TIMING
+  if ((tid & 31) == 0)
+    for (int q = 0; q < 8; ++q) atomicAdd(&g_phase_cycles[tid >> 5][q], (unsigned long long)t_acc[q]);
+#endif
 }
 
 __global__ void __launch_bounds__(128)
@@ -174,7 +226,6 @@ struct maf_handle {
   BoundaryTables BT{};
   GatherTables G{};
   bool gather_ready = false;
-  int16_t* d_task_ij = nullptr;
   int32_t* d_order = nullptr;   // processing order of the elements of [e0, e1)
   int nij = 0;
   double *d_xms = nullptr, *d_cps = nullptr, *d_r = nullptr, *d_nz = nullptr, *d_rn = nullptr, *d_part = nullptr;
@@ -303,7 +354,6 @@ static void ensure_gather(maf_handle* h) {
   fill_gather_tables(GH, h->G);
   if (GH.nij > MAF_MAX_NIJ) throw std::runtime_error("too many dof-block classes for the gather kernel");
   h->G.npairs = S.npairs;
-  h->d_task_ij = upload(h, GH.task_ij.data(), GH.task_ij.size());
   h->gather_ready = true;
 }
 
@@ -335,7 +385,7 @@ static void launch_atomic_range(maf_handle* h, const double* d_xms, const double
   const int64_t ne = e1 - e0;
   if (ne <= 0) return;
   const int grid = (int)std::min<int64_t>(ne, (int64_t)h->grid);
-  StageSink st{nullptr, nullptr, nullptr, 0};
+  StageSink st{nullptr, nullptr, 0};
   kern<<<grid, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, d_order, e0, e1);
   CU(cudaGetLastError());
   h->launches += 1;
@@ -364,7 +414,7 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
   (void)timed;
   h->timed_valid = false;
   CU(cudaEventRecord(h->ev[1], s));
-  StageSink st{nullptr, nullptr, nullptr, 0};
+  StageSink st{nullptr, nullptr, 0};
   if (mode == MAF_SCATTER_ATOMIC) {
     // only what this element range touches (contiguous, because unknowns are numbered node-major)
     CU(cudaMemsetAsync(d_r + h->eq_lo, 0, sizeof(double) * (size_t)(h->eq_hi - h->eq_lo), s));
@@ -372,7 +422,7 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
   } else {
     ensure_gather(h);
     ensure_stage(h);
-    st = StageSink{h->d_kel, h->d_rel, h->d_task_ij, h->nij};
+    st = StageSink{h->d_kel, h->d_rel, h->nij};
   }
   CU(cudaEventRecord(h->ev[6], s));
   if (ne > 0) {
@@ -490,6 +540,8 @@ int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* pa
     h->T.elpair = upload(h, M.sym.elpair.data(), M.sym.elpair.size());
     h->T.pairoff = upload(h, M.sym.pairoff.data(), M.sym.pairoff.size());
     h->T.eq0 = upload(h, M.sym.eq0.data(), M.sym.eq0.size());
+    h->T.nodecol = upload(h, M.nodecol.data(), M.nodecol.size());
+    h->T.nodemask32 = upload(h, M.nodemask32.data(), M.nodemask32.size());
     h->T.utab = M.utab.empty() ? nullptr : upload(h, M.utab.data(), M.utab.size());
     h->T.numnp = M.numnp; h->T.numel = M.numel; h->T.num1el = M.num1el; h->T.nuel1 = M.nuel1;
     h->BT.edge1 = upload(h, M.edge1.data(), M.edge1.size());
@@ -743,6 +795,28 @@ int maf_range_info(maf_handle* h, int64_t* out8) {
   out8[4] = h->eq_lo + 1; out8[5] = h->eq_hi;        // rows of r touched
   out8[6] = h->slot_lo + 1; out8[7] = h->slot_hi;    // entries of nzval touched
   MAF_API_END(h)
+}
+
+// profiling builds (-DMAF_PHASE_TIMING): cycles per warp and phase [warp][8] summed over the CTAs since the last
+// call: wait@gather, interp, wait, gauss, wait, gather-next, residual+tangent, -; then from out[32] the cycles per
+// tangent chunk. Returns 1 in regular builds.
+int maf_debug_phase_cycles(unsigned long long* out, int n) {
+#ifdef MAF_PHASE_TIMING
+  unsigned long long hbuf[MAF_NT / 32][8];
+  if (cudaMemcpyFromSymbol(hbuf, g_phase_cycles, sizeof(hbuf)) != cudaSuccess) return 2;
+  for (int q = 0; q < n && q < (int)(sizeof(hbuf) / 8); ++q) out[q] = (&hbuf[0][0])[q];
+  std::memset(hbuf, 0, sizeof(hbuf));
+  if (cudaMemcpyToSymbol(g_phase_cycles, hbuf, sizeof(hbuf)) != cudaSuccess) return 2;
+  unsigned long long cbuf[MAF_MAX_CHUNKS];   // out[32 ...]: cycles per tangent chunk
+  if (cudaMemcpyFromSymbol(cbuf, maf::g_chunk_cycles, sizeof(cbuf)) != cudaSuccess) return 2;
+  for (int q = 0; q < MAF_MAX_CHUNKS && 32 + q < n; ++q) out[32 + q] = cbuf[q];
+  std::memset(cbuf, 0, sizeof(cbuf));
+  if (cudaMemcpyToSymbol(maf::g_chunk_cycles, cbuf, sizeof(cbuf)) != cudaSuccess) return 2;
+  return 0;
+#else
+  (void)out; (void)n;
+  return 1;
+#endif
 }
 
 int maf_fp64_peak(int device, double* tflops) {

@@ -18,9 +18,17 @@ inline int kind_of(int nr, int nc) {
     if (tab[k][0] == nr && tab[k][1] == nc) return k;
   throw std::runtime_error("no block_accumulate instantiation for this block shape");
 }
-inline int kind_cost(int kind) {
+// Cost of one task (9 outputs) for the warp schedule: FP64 operations per Gauss point plus the fixed part
+// (set-up, loop latency, scatter), in the same unit; MAF_TASK_FIXED was fitted to the measured cycles per chunk
+// (profiling build, tools/profile_once.py): the short blocks cost far more than their arithmetic.
+#ifndef MAF_TASK_FIXED
+#define MAF_TASK_FIXED 37
+#endif
+inline int kind_cost(int kind, bool fused) {
   static const int tab[8][2] = {{1, 1}, {1, 2}, {1, 3}, {2, 1}, {2, 2}, {3, 5}, {5, 5}, {6, 5}};
-  return 3 * tab[kind][0] * tab[kind][1] + 27 * tab[kind][1];
+  if (fused) return MAF_TASK_FIXED + 107;
+  if (tab[kind][1] == 5) return MAF_TASK_FIXED + 5 * tab[kind][0] + 8 + 42;   // sum-factorised mesh-column blocks
+  return MAF_TASK_FIXED + tab[kind][0] * tab[kind][1] + 9 * tab[kind][1];
 }
 
 // dofs8: column (1-based) of vx vy vz vmx vmy vmz lambda pm, or 0 (Mesh.dofs, Bc.jl:414-431)
@@ -50,7 +58,12 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
     throw std::runtime_error("the mesh pressure is a dof exactly for ALEV/ALEVB");
 
   const int vr0 = pn != 0.0 ? 0 : 1, vnr = pn != 0.0 ? 6 : 5;
-  struct B { int f, g, c0, nr, d0, nc, db; };
+  // ALEVB: the mesh equations are the membrane equations with the viscous stress of the mesh velocity, no surface
+  // tension and the mesh pressure as normal load (GeoDynStress.jl:156-159, FiniteElement.jl:304-313): the bending and
+  // moment tangent of the v rows and of the vm rows w.r.t. the mesh dofs coincide. Without a normal pressure on the
+  // v rows both blocks are produced by one fused task from A_m and the 2 x 2 corner difference d(S_v - S_m).
+  cfg.fused_vm = (motion == M_ALEVB && pn == 0.0) ? 1 : 0;
+  struct B { int f, g, c0, nr, d0, nc, db, notask, fused; };
   std::vector<B> bl;
   switch (motion) {
     case M_STATIC:
@@ -72,6 +85,10 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
             {F_P, F_V, 0, 1, 0, 1, 0}, {F_P, F_M, 0, 1, 0, 3, 0}, {F_P, F_P, 0, 1, 0, 1, 1}};
       break;
     default: throw std::runtime_error("unknown motion code");
+  }
+  if (cfg.fused_vm) {
+    bl[1] = B{F_V, F_M, 1, 2, 1, 2, 0, 1, 0};   // corner difference only, consumed by the fused block
+    bl[3].fused = 1;
   }
   // row channel range per field = union over its blocks; column ranges are per block
   int rlo[NFIELD], rhi[NFIELD];
@@ -109,29 +126,42 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
     const B& b = bl[k];
     const bool q = is_mesh(b) && (b.f == F_V || (b.f == F_M && motion == M_ALEVB));
     cfg.blocks[k] = Block{(int8_t)b.f, (int8_t)b.g, (int8_t)b.c0, (int8_t)b.nr, (int8_t)b.d0, (int8_t)b.nc,
-                          (int8_t)kind_of(b.nr, b.nc), (int8_t)b.db, (int8_t)(is_mesh(b) ? 1 : 0), (int8_t)(q ? 1 : 0)};
+                          (int8_t)kind_of(b.nr, b.nc), (int8_t)b.db, (int8_t)(is_mesh(b) ? 1 : 0), (int8_t)(q ? 1 : 0),
+                          (int8_t)b.notask, (int8_t)b.fused};
   }
-  // tangent tasks, heaviest kinds first so that the lanes of a warp share a code path
-  std::vector<Task> tasks;
-  std::vector<int> order(cfg.nblocks);
-  for (int k = 0; k < cfg.nblocks; ++k) order[k] = k;
-  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-    const int cx = kind_cost(cfg.blocks[x].kind), cy = kind_cost(cfg.blocks[y].kind);
-    return cx != cy ? cx > cy : cfg.blocks[x].kind < cfg.blocks[y].kind;
-  });
-  for (int k : order) {
+  // present components of every field; (row dof, col dof) classes of the deterministic staging rows,
+  // in destination order (J, then I)
+  for (int f = 0; f < NFIELD; ++f) {
+    cfg.npc[f] = 0;
+    for (int i = 0; i < cfg.ncomp[f]; ++i)
+      if (cfg.fdof[f][i] >= 0) cfg.pcomp[f][cfg.npc[f]++] = (int8_t)i;
+  }
+  {
+    bool has[64] = {false};
+    for (int k = 0; k < cfg.nblocks; ++k)
+      for (int ii = 0; ii < cfg.npc[bl[k].f]; ++ii)
+        for (int jj = 0; jj < cfg.npc[bl[k].g]; ++jj)
+          has[8 * cfg.fdof[bl[k].f][cfg.pcomp[bl[k].f][ii]] + cfg.fdof[bl[k].g][cfg.pcomp[bl[k].g][jj]]] = true;
+    int nij = 0;
+    for (int J = 0; J < 8; ++J)
+      for (int I = 0; I < 8; ++I) cfg.ij_of[8 * I + J] = has[8 * I + J] ? (int8_t)nij++ : (int8_t)-1;
+  }
+  // tangent chunks: <= 32 consecutive tasks of one block
+  struct Ch { int blk, first, count, cost; };
+  std::vector<Ch> chs;
+  cfg.ntasks = 0;
+  for (int k = 0; k < cfg.nblocks; ++k) {
     const Block& b = cfg.blocks[k];
-    for (int i = 0; i < cfg.ncomp[b.f]; ++i) {
-      if (cfg.fdof[b.f][i] < 0) continue;
-      for (int j = 0; j < cfg.ncomp[b.g]; ++j) {
-        if (cfg.fdof[b.g][j] < 0) continue;
-        for (int a2 = 0; a2 < 3; ++a2) tasks.push_back(Task{(uint8_t)k, (uint8_t)i, (uint8_t)j, (uint8_t)a2});
-      }
-    }
+    if (b.notask) continue;
+    const int nt = 9 * cfg.npc[b.f] * cfg.npc[b.g];
+    if (nt == 0) continue;
+    if (nt > 255) throw std::runtime_error("task index overflow");
+    cfg.ntasks += nt;
+    const int parts = (nt + 31) / 32, per = (nt + parts - 1) / parts;
+    for (int first = 0; first < nt; first += per)
+      chs.push_back(Ch{k, first, std::min(per, nt - first), kind_cost(b.kind, b.fused != 0)});
   }
-  if ((int)tasks.size() > MAF_MAX_TASKS) throw std::runtime_error("task table overflow");
-  cfg.ntasks = (int)tasks.size();
-  for (int k = 0; k < cfg.ntasks; ++k) cfg.tasks[k] = tasks[k];
+  if ((int)chs.size() > MAF_MAX_CHUNKS) throw std::runtime_error("chunk table overflow");
 
   // Gauss-point work items: GEO_A (6 per gp) when the mesh moves, GEO_B (1 per gp), LIN (1 per gp)
   std::vector<Item> items;
@@ -203,17 +233,29 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
     schedule(cls, cost, {}, -1, cfg.item_slot, cfg.item_rounds);
   }
   {
-    std::vector<int> cls(cfg.ntasks), cost(cfg.ntasks);
-    for (int k = 0; k < cfg.ntasks; ++k) {
-      cls[k] = cfg.blocks[cfg.tasks[k].blk].kind;
-      cost[k] = kind_cost(cls[k]);
+    // chunks of tangent tasks: longest-processing-time first over the warps. During the tangent phase the first
+    // warps also form the element residual (72 rows over the first 72 threads): account for that work when
+    // balancing.
+    std::stable_sort(chs.begin(), chs.end(), [](const Ch& x, const Ch& y) { return x.cost > y.cost; });
+    cfg.nchunks = (int)chs.size();
+    for (int k = 0; k < cfg.nchunks; ++k)
+      cfg.chunks[k] = Chunk{(uint8_t)chs[k].blk, (uint8_t)chs[k].first, (uint8_t)chs[k].count, 0};
+    std::vector<int> load(nwarps, 0);
+    for (int w = 0; w < nwarps && w < 3; ++w) load[w] = 30;
+    std::vector<std::vector<int>> plan(nwarps);
+    for (int k = 0; k < cfg.nchunks; ++k) {
+      int wbest = 0;
+      for (int w = 1; w < nwarps; ++w)
+        if (load[w] < load[wbest]) wbest = w;
+      plan[wbest].push_back(k);
+      load[wbest] += chs[k].cost;
     }
-    // during the tangent phase the first warps also form the element residual (72 rows over the first 72 threads):
-    // account for that work when balancing the warps
-    std::vector<int> init(nwarps, 0);
-    for (int w = 0; w < nwarps && w < 3; ++w) init[w] = 60;
-    init[nwarps - 1] += 130;   // the last warp gathers the next element during the tangent phase
-    schedule(cls, cost, init, -1, cfg.task_slot, cfg.task_rounds);
+    cfg.task_rounds = 0;
+    for (int w = 0; w < nwarps; ++w) cfg.task_rounds = std::max(cfg.task_rounds, (int)plan[w].size());
+    if (cfg.task_rounds > MAF_MAX_ROUNDS || nwarps > 8) throw std::runtime_error("chunk slot table overflow");
+    for (int q = 0; q < MAF_MAX_ROUNDS * 8; ++q) cfg.chunk_slot[q] = -1;
+    for (int w = 0; w < nwarps; ++w)
+      for (size_t r = 0; r < plan[w].size(); ++r) cfg.chunk_slot[r * nwarps + w] = (int8_t)plan[w][r];
   }
 
   // rows present in the pattern of a column of dof J
@@ -246,21 +288,20 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   cfg.o_tdb = o; o += 82;
   cfg.o_int = o; o += (I_PAIR + 1) / 2;   // node ids, equation numbers, active-dof masks
   o += o & 1;
-  cfg.o_slot = o; o += 36;
+  cfg.o_slot = o; o += 72;                // column pointers of (node b, dof J), int64
   cfg.o_po = o; o += 81;
   o += o & 1;
-  cfg.o_base = o; o += 2;
   cfg.front_doubles = o;
-  // back block (offsets relative to sm + 2 * front_doubles)
+  // back block (offsets relative to sm + 2 * front_doubles + 2 * MAF_IDS_DOUBLES: two ids buffers in between)
   o = 0;
   cfg.o_E = o; o += 9 * E_STRIDE;
   cfg.o_S = o; o += 9 * S_STRIDE;
   cfg.o_G = o; o += 9 * G_STRIDE;
   o += o & 1;
   cfg.o_A = o; o += 9 * cfg.asize;
-  cfg.smem_doubles = 2 * cfg.front_doubles + o;
+  cfg.smem_doubles = 2 * cfg.front_doubles + 2 * MAF_IDS_DOUBLES + o;
   // everything that is read with 16-byte loads must sit on an even double offset
-  bool ok = !(cfg.o_A & 1) && !(cfg.o_phi & 1) && !(cfg.o_FG & 1) && !(cfg.asize & 1) && !(cfg.o_base & 1) &&
+  bool ok = !(cfg.o_A & 1) && !(cfg.o_phi & 1) && !(cfg.o_FG & 1) && !(cfg.asize & 1) &&
             !(cfg.front_doubles & 1) && !(cfg.o_po & 1);
   for (int f = 0; f < NFIELD; ++f) {
     ok = ok && !(cfg.aoff[f] & 1) && !(cfg.ald[f] & 1) && (cfg.bcol[f] < 0 || !(cfg.bcol[f] & 1));

@@ -10,8 +10,15 @@
 // is merged into the column of the dof that moves the mesh (FiniteElement.jl:118-123).
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include "maf_math.cuh"
+
+#ifndef MAF_SMALL_UNROLL
+#define MAF_SMALL_UNROLL 1
+#endif
+constexpr int kSmallUnroll = MAF_SMALL_UNROLL;
+#define MAF_NT 128  // threads per CTA of the area kernel (one element per CTA iteration)
 
 namespace maf {
 
@@ -26,18 +33,24 @@ struct Block {      // one (row field, col field) tangent block type
   int8_t db;        // add the Dohrmann-Bochev matrix (lambda-lambda and pm-pm blocks)
   int8_t mesh;      // columns are the dofs that move the mesh, incl. the second-derivative channels N11,N22,N12
   int8_t qterm;     // mesh block whose rows carry the moment term -Q_k Gamma^mu_k (v rows; vm rows for ALEVB)
+  int8_t notask;    // storage only: its entries are consumed by the fused block (ALEVB corner differences)
+  int8_t fused;     // (vm, mesh) block that also produces the (v, mesh) block (shared bending tangent, ALEVB)
 };
-struct Task {       // 27 outputs of one block: rows (a1 = 0..2, a2), all 9 column nodes b
-  uint8_t blk, i, j, a2;
+// A tangent task = the 9 entries K_el[(a,I),(b,J)], b = 0..8, of one (block, row comp i, col comp j, row node a),
+// accumulated over the 9 Gauss points in registers. Tasks of a block are numbered t = a + 9 (jj + npc[g] ii) over
+// the PRESENT components; a chunk is <= 32 consecutive tasks of one block, executed by the lanes of one warp.
+struct Chunk {
+  uint8_t blk, first, count, pad;
 };
 struct Item {       // phase-G work item of one Gauss point
   uint8_t type, gp, gamma, j;
 };
 
-#define MAF_MAX_BLOCKS 12
-#define MAF_MAX_TASKS 160
+#define MAF_MAX_BLOCKS 14
+#define MAF_MAX_CHUNKS 48
+#define MAF_MAX_ROUNDS 16
 #define MAF_MAX_ITEMS 96
-#define MAF_MAX_SLOTS 512
+#define MAF_MAX_SLOTS 256
 
 struct Config {
   int motion, ndf;
@@ -55,20 +68,25 @@ struct Config {
   int asize;                      // doubles per Gauss point
   int nblocks;
   Block blocks[MAF_MAX_BLOCKS];
-  int ntasks;
-  Task tasks[MAF_MAX_TASKS];
+  int ntasks;                     // total number of tangent tasks (diagnostics)
+  int nchunks;
+  Chunk chunks[MAF_MAX_CHUNKS];
+  int npc[NFIELD];                // present components per field and their indices
+  int8_t pcomp[NFIELD][3];
+  int8_t ij_of[64];               // deterministic path: staging column of the (row dof I, col dof J) class, -1 none
+  int fused_vm;                   // ALEVB with pn = 0: the v rows share the bending tangent of the vm rows
   int nitems;
   Item items[MAF_MAX_ITEMS];
   // thread -> work maps (host-built so that lanes of a warp share the code path): slot s of round r
   int nthreads;                   // threads per element
   int item_rounds, task_rounds;
   int16_t item_slot[MAF_MAX_SLOTS];   // [round][tid] -> item id or -1
-  int16_t task_slot[MAF_MAX_SLOTS];   // [round][tid] -> task id or -1
+  int8_t chunk_slot[MAF_MAX_ROUNDS * 8];  // [round][warp] -> chunk id or -1
   uint8_t rowmask[8];             // per column dof J: bitmask of row dofs I whose block is in the pattern
   Material mat;
   double dbscale;                 // adb / zv
   // shared-memory layout (offsets in doubles from the element's block)
-  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_G, o_A, o_int, o_slot, o_po, o_base, o_FG, o_tdb, front_doubles, smem_doubles;
+  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_G, o_A, o_int, o_slot, o_po, o_FG, o_tdb, front_doubles, smem_doubles;
 };
 
 // interpolated Gauss-point inputs E[gp][.]
@@ -94,6 +112,8 @@ struct Tables {
   const int32_t* elpair;    // numel x 81: index of (A = node a, B = node b) in the node-adjacency list of B
   const uint8_t* pairoff;   // npairs x 8: rows that precede node A's rows in column (B,J)
   const int32_t* eq0;       // numnp: an equation number whose column pointer bounds the node's columns from below
+  const int64_t* nodecol;   // numnp x 8: colptr[ID[J, node]], -1 for inactive dofs
+  const int32_t* nodemask32;  // nodemask as int32 (the granularity of an asynchronous copy)
   const double* utab;       // (nuel1*nuel2) x BASIS_DOUBLES precomputed basis blocks, or NULL (built per element)
   int64_t numnp, numel;
   int num1el, nuel1;
@@ -102,7 +122,6 @@ struct Tables {
 // shared-memory basis table: Phi[gp][c][a2][4] (node a = a1 + 3 a2 at 4 a2 + a1; the pad keeps the three values
 // of a node row 16-byte aligned so that they load as LDS.128 + LDS.64)
 enum { PHI_C = 12, PHI_GP = 72, PHI_DOUBLES = 9 * 72, FG_STRIDE = 18, BASIS_DOUBLES = 9 * 72 + 9 * 18 + 10 + 82 };  // Phi | FG | w | tdb
-#define SLOT_NONE (-2147483647 - 1)
 MAF_HD int phi_a(int a) { return 4 * (a / 3) + (a % 3); }
 struct alignas(16) dbl2 { double x, y; };
 MAF_HD dbl2 ld2(const double* p) { return *reinterpret_cast<const dbl2*>(p); }
@@ -126,6 +145,25 @@ MAF_HD int popc8(unsigned x) {
   return __popc(x);
 #else
   return __builtin_popcount(x);
+#endif
+}
+
+MAF_HD long long dbl_bits(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double_as_longlong(x);
+#else
+  long long b;
+  memcpy(&b, &x, 8);
+  return b;
+#endif
+}
+MAF_HD double bits_dbl(long long b) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(b);
+#else
+  double x;
+  memcpy(&x, &b, 8);
+  return x;
 #endif
 }
 
@@ -158,81 +196,110 @@ MAF_HD void build_basis_block(int tid, int nt, const double* l1, const double* l
 // Phase 0: gather the element's nodal data, integer maps and basis table into shared memory.
 // FiniteElement.jl:100-101 (xms_el, cps_el), Mesh.jl:311-319 (table lookup by unique element).
 // ---------------------------------------------------------------------------------------------------------
-MAF_HD void phase_gather(int tid, int nt, const Config& cfg, const Tables& T, int64_t el, const double* xms,
-                         const double* cps, double* fr /* front block of this element */) {
+// The gather never passes through registers: every datum is an asynchronous global -> shared copy (cp.async /
+// LDGSTS), issued at the top of the iteration of the PREVIOUS element of the CTA and awaited at its end, so its
+// latency is hidden behind a whole element and it costs no registers in the compute phases. It is split by
+// dependency level and software-pipelined over the elements k, k + G, k + 2G, ... of the CTA (maf_api.cu):
+//   level 1 (gather_ids_async)   node ids, pair ids, unique-element ids of element k + 2G -> ids buffer
+//   level 2 (gather_data_async)  nodal data, equation numbers, column pointers, pairoff rows, basis block of
+//                                element k + G (addresses from the ids buffer filled one iteration earlier)
+// ids buffer (int32): [0,9) node ids | [9,90) pair ids of (a,b) | 90, 91: unique-element id per direction
+#define MAF_IDS_INTS 92
+#define MAF_IDS_DOUBLES 46
+MAF_HD void async_copy4(void* sdst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+#else
+  memcpy(sdst, gsrc, 4);
+#endif
+}
+MAF_HD void async_copy8(void* sdst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+#else
+  memcpy(sdst, gsrc, 8);
+#endif
+}
+MAF_HD void async_copy16(void* sdst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+#else
+  memcpy(sdst, gsrc, 16);
+#endif
+}
+MAF_HD void async_wait_all() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+// slots that no copy ever writes: control points of absent dofs read as zero (GeoDynStress.jl:196-202), equation
+// numbers of dofs beyond ndf are "inactive". Once per front buffer.
+MAF_HD void gather_init(int tid, const Config& cfg, double* fr) {
   int32_t* si = reinterpret_cast<int32_t*>(fr + cfg.o_int);
-  const int64_t np = T.numnp;
-  for (int k = tid; k < 9 * 13; k += nt) {
-    const int a = k % 9, q = k / 9;
-    const int64_t node = T.IX[9 * el + a];
-    if (q < 3) {
-      fr[cfg.o_x + 9 * q + a] = xms[node + np * q];
-    } else if (q < 11) {
-      // q-3 enumerates (field, comp): v0 v1 v2 m0 m1 m2 l p
-      const int u = q - 3;
-      const int f = u < 3 ? F_V : (u < 6 ? F_M : (u == 6 ? F_L : F_P));
-      const int i = u < 6 ? u % 3 : 0;
-      const int dof = cfg.fdof[f][i];
-      const double val = dof >= 0 ? cps[node + np * dof] : 0.0;  // absent dofs read as zero (GeoDynStress.jl:196-202)
-      const int base = f == F_V ? cfg.o_cv : (f == F_M ? cfg.o_cm : (f == F_L ? cfg.o_cl : cfg.o_cp));
-      fr[base + 9 * i + a] = val;
-    } else if (q == 11) {
-      si[I_NODE + a] = (int32_t)node;
-      si[I_MASK + a] = T.nodemask[node];
-    } else {
-      for (int d = 0; d < 8; ++d) si[I_EQ + 8 * a + d] = d < cfg.ndf ? T.ID[(int64_t)cfg.ndf * node + d] : -1;
-    }
-  }
-  // scatter map of this element, looked up once:
-  //   slot(a, I; b, J) = base + cprel[8 b + J] + po[(9 a + b) * 8 + J] + rank(I | a, J)
-  // base = a column pointer that bounds the element's columns from below, cprel = column pointer of (b, J)
-  // relative to it (int32; SLOT_NONE for a Dirichlet column), po = the pairoff row of the node pair (a, b).
-  int32_t* cprel = reinterpret_cast<int32_t*>(fr + cfg.o_slot);
-  unsigned long long* po = reinterpret_cast<unsigned long long*>(fr + cfg.o_po);
-  const int64_t base = T.colptr[T.eq0[T.IX[9 * el]]];
-  for (int k = tid; k < 72 + 81; k += nt) {
-    if (k < 72) {
-      const int b = k >> 3, J = k & 7;
-      int32_t rel = SLOT_NONE;   // columns exist only for active dofs (FiniteElement.jl:111)
-      if (J < cfg.ndf) {
-        const int32_t eq = T.ID[(int64_t)cfg.ndf * T.IX[9 * el + b] + J];
-        if (eq >= 0) rel = (int32_t)(T.colptr[eq] - base);
-      }
-      cprel[k] = rel;
-    } else {
-      po[k - 72] = *reinterpret_cast<const unsigned long long*>(T.pairoff + (int64_t)T.elpair[81 * el + (k - 72)] * 8);
-    }
-  }
-  if (tid == 0) *reinterpret_cast<int64_t*>(fr + cfg.o_base) = base;
-  // basis block of this element: Phi[gp][c][a2][4] | FG[gp][18] | w[9]   (contiguous, BASIS_DOUBLES)
-  const int e1 = (int)(el % T.num1el), e2 = (int)(el / T.num1el);
-  if (T.utab) {   // precomputed per unique element (same products, formed once on the host): straight copy
-    const dbl2* src = reinterpret_cast<const dbl2*>(T.utab + (size_t)BASIS_DOUBLES * (T.uel1[e1] + (size_t)T.nuel1 * T.uel2[e2]));
-    dbl2* dst = reinterpret_cast<dbl2*>(fr + cfg.o_phi);
-    for (int k = tid; k < BASIS_DOUBLES / 2; k += nt) dst[k] = src[k];
-  } else {
-    build_basis_block(tid, nt, T.line1 + 30 * T.uel1[e1], T.line2 + 30 * T.uel2[e2],
-                      T.tdb + 81 * ((int64_t)T.uel1[e1] + (int64_t)T.nuel1 * T.uel2[e2]), fr + cfg.o_phi);
+  for (int k = tid; k < 72; k += MAF_NT) {
+    const int u = k / 9, a = k % 9;
+    const int f = u < 3 ? F_V : (u < 6 ? F_M : (u == 6 ? F_L : F_P));
+    const int i = u < 6 ? u % 3 : 0;
+    const int fb = f == F_V ? cfg.o_cv : (f == F_M ? cfg.o_cm : (f == F_L ? cfg.o_cl : cfg.o_cp));
+    if (cfg.fdof[f][i] < 0) fr[fb + 9 * i + a] = 0.0;
+    if ((k & 7) >= cfg.ndf) si[I_EQ + k] = -1;
   }
 }
 
-// L2 prefetch of what the next element of this CTA will gather (device only; a no-op on the host)
-MAF_HD void prefetch_next(int lane, const Config& cfg, const Tables& T, int64_t el, const double* xms,
-                          const double* cps) {
-#if defined(__CUDA_ARCH__)
-  if (el >= T.numel) return;
-  if (lane < 9) {
-    const int64_t node = T.IX[9 * el + lane];
-    for (int q = 0; q < 3; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(xms + node + T.numnp * q));
-    for (int q = 0; q < cfg.ndf; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(cps + node + T.numnp * q));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(T.ID + (int64_t)cfg.ndf * node));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(T.nodemask + node));
-  } else if (lane < 13) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(T.elpair + 81 * el + 32 * (lane - 9)));
+MAF_HD void gather_ids_async(int tid, const Tables& T, int64_t el, int32_t* ids) {
+  if (tid < 9) async_copy4(ids + tid, T.IX + 9 * el + tid);
+  else if (tid < 90) async_copy4(ids + tid, T.elpair + 81 * el + (tid - 9));
+  else if (tid == 90) async_copy4(ids + 90, T.uel1 + (el % T.num1el));
+  else if (tid == 91) async_copy4(ids + 91, T.uel2 + (el / T.num1el));
+}
+
+// Work items k: [0,27) x | [27,99) control points (8 dof slots) | [99,108) active-dof mask | [108,180) equation
+// numbers | [180,252) column pointers of (node b, dof J) | [252,333) pairoff row of the node pair (a,b); then the
+// basis block Phi[gp][c][a2][4] | FG[gp][18] | w[9] | tdb of the (unique) element in 16-byte pieces.
+// Scatter map of the element, looked up once:
+//   slot(a, I; b, J) = col[8 b + J] + po[(9 a + b) * 8 + J] + rank(I | a, J)
+// col = column pointer of (b, J) (negative for a Dirichlet column), po = the pairoff row of the node pair (a, b).
+#define MAF_GATHER_ITEMS 333
+MAF_HD void gather_data_async(int tid, const Config& cfg, const Tables& T, const int32_t* ids, const double* xms,
+                              const double* cps, double* fr /* front block of the element */) {
+  int32_t* si = reinterpret_cast<int32_t*>(fr + cfg.o_int);
+  long long* col = reinterpret_cast<long long*>(fr + cfg.o_slot);
+  unsigned long long* po = reinterpret_cast<unsigned long long*>(fr + cfg.o_po);
+  const int64_t np = T.numnp;
+  const int ndf = cfg.ndf;
+#pragma unroll
+  for (int r = 0; r < (MAF_GATHER_ITEMS + MAF_NT - 1) / MAF_NT; ++r) {
+    const int k = tid + MAF_NT * r;
+    if (k < 27) {
+      async_copy8(fr + cfg.o_x + k, xms + ids[k % 9] + np * (k / 9));
+    } else if (k < 99) {   // (k-27)/9 enumerates (field, comp): v0 v1 v2 m0 m1 m2 l p
+      const int u = (k - 27) / 9, a = k % 9;
+      const int f = u < 3 ? F_V : (u < 6 ? F_M : (u == 6 ? F_L : F_P));
+      const int i = u < 6 ? u % 3 : 0;
+      const int dof = cfg.fdof[f][i];
+      const int fb = f == F_V ? cfg.o_cv : (f == F_M ? cfg.o_cm : (f == F_L ? cfg.o_cl : cfg.o_cp));
+      if (dof >= 0) async_copy8(fr + fb + 9 * i + a, cps + ids[a] + np * dof);
+    } else if (k < 108) {
+      async_copy4(si + I_MASK + (k - 99), T.nodemask32 + ids[k - 99]);
+    } else if (k < 180) {
+      const int a = (k - 108) >> 3, d = (k - 108) & 7;
+      if (d < ndf) async_copy4(si + I_EQ + (k - 108), T.ID + (int64_t)ndf * ids[a] + d);
+    } else if (k < 252) {
+      async_copy8(col + (k - 180), T.nodecol + 8 * (int64_t)ids[(k - 180) >> 3] + ((k - 180) & 7));
+    } else if (k < MAF_GATHER_ITEMS) {
+      async_copy8(po + (k - 252), T.pairoff + (int64_t)ids[9 + (k - 252)] * 8);
+    }
   }
-#else
-  (void)lane; (void)cfg; (void)T; (void)el; (void)xms; (void)cps;
-#endif
+  const int u1 = ids[90], u2 = ids[91];
+  if (T.utab) {   // precomputed per unique element (the same products, formed once on the host): straight copy
+    const dbl2* src = reinterpret_cast<const dbl2*>(T.utab + (size_t)BASIS_DOUBLES * (u1 + T.nuel1 * u2));
+    dbl2* dst = reinterpret_cast<dbl2*>(fr + cfg.o_phi);
+    for (int k = tid; k < BASIS_DOUBLES / 2; k += MAF_NT) async_copy16(dst + k, src + k);
+  } else {        // too many unique elements for a table: formed here from the 1-D tables
+    build_basis_block(tid, MAF_NT, T.line1 + 30 * u1, T.line2 + 30 * u2,
+                      T.tdb + 81 * ((int64_t)u1 + (int64_t)T.nuel1 * u2), fr + cfg.o_phi);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -288,7 +355,9 @@ MAF_HD void store_column(const Config& cfg, double* Agp, double w, const GpStres
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int c = 0; c < NCH; ++c)
-        if (c >= c0 && c < c0 + nr) Agp[base + (i * nr + (c - c0)) * ld] = w * der(S.Sv[c][i]);
+        if (c >= c0 && c < c0 + nr)
+          Agp[base + (i * nr + (c - c0)) * ld] =
+              w * ((cfg.fused_vm && g == cfg.mesh_field) ? der(S.Sv[c][i]) - der(S.Sm[c][i]) : der(S.Sv[c][i]));
   }
   if (has_col(cfg, F_M, g, d)) {
     const int base = a_index(cfg, F_M, 0, cfg.rc0[F_M], g, j, d), ld = cfg.ald[F_M], nr = cfg.rnc[F_M], c0 = cfg.rc0[F_M];
@@ -536,35 +605,30 @@ MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const double* fr,
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Phase 3b: one tangent task = 27 entries of K_el (rows a = a1 + 3 a2, a1 = 0..2; all column nodes b)
-// of one (row dof I, col dof J) block, accumulated over the 9 Gauss points in registers.
+// Phase 3b: tangent tasks. Each task keeps 9 (fused: 18) accumulators in registers over the 9 Gauss points:
+//   first contraction  u[d]  = sum_c Phi^c_a A[(i,c)][(j,d)]
+//   second contraction K[b] += sum_d u[d] Phi^d_b
 // ---------------------------------------------------------------------------------------------------------
 template <int NR, int NC>
 MAF_HD void block_accumulate(const double* __restrict__ A0, int asize, int ald, const double* __restrict__ Phi,
-                             int c0, int d0, int a2, double acc[3][9]) {
+                             int c0, int d0, int a, double acc[9]) {
 #pragma unroll
-  for (int a1 = 0; a1 < 3; ++a1)
-#pragma unroll
-    for (int b = 0; b < 9; ++b) acc[a1][b] = 0.0;
+  for (int b = 0; b < 9; ++b) acc[b] = 0.0;
+  const int pa = phi_a(a);
+  // the blocks of the first-derivative channels are short: three Gauss points per trip so that the loads of one
+  // overlap the arithmetic of the others (a trip of one point is all shared-memory latency)
+#pragma unroll kSmallUnroll
   for (int gp = 0; gp < 9; ++gp) {
     const double* Ag = A0 + (size_t)asize * gp;
     const double* Pg = Phi + PHI_GP * gp;
-    double u[3][NC];
+    double u[NC];
 #pragma unroll
-    for (int a1 = 0; a1 < 3; ++a1)
-#pragma unroll
-      for (int d = 0; d < NC; ++d) u[a1][d] = 0.0;
+    for (int d = 0; d < NC; ++d) u[d] = 0.0;
 #pragma unroll
     for (int c = 0; c < NR; ++c) {
-      const dbl2 p01 = ld2(Pg + PHI_C * (c0 + c) + 4 * a2);
-      const double p2 = Pg[PHI_C * (c0 + c) + 4 * a2 + 2];
+      const double p = Pg[PHI_C * (c0 + c) + pa];
 #pragma unroll
-      for (int d = 0; d < NC; ++d) {
-        const double av = Ag[c * ald + d];
-        u[0][d] += p01.x * av;
-        u[1][d] += p01.y * av;
-        u[2][d] += p2 * av;
-      }
+      for (int d = 0; d < NC; ++d) u[d] += p * Ag[c * ald + d];
     }
 #pragma unroll
     for (int d = 0; d < NC; ++d)
@@ -572,14 +636,17 @@ MAF_HD void block_accumulate(const double* __restrict__ A0, int asize, int ald, 
       for (int b2 = 0; b2 < 3; ++b2) {
         const dbl2 q01 = ld2(Pg + PHI_C * (d0 + d) + 4 * b2);
         const double q2 = Pg[PHI_C * (d0 + d) + 4 * b2 + 2];
-#pragma unroll
-        for (int a1 = 0; a1 < 3; ++a1) {
-          acc[a1][3 * b2] += u[a1][d] * q01.x;
-          acc[a1][3 * b2 + 1] += u[a1][d] * q01.y;
-          acc[a1][3 * b2 + 2] += u[a1][d] * q2;
-        }
+        acc[3 * b2] += u[d] * q01.x;
+        acc[3 * b2 + 1] += u[d] * q01.y;
+        acc[3 * b2 + 2] += u[d] * q2;
       }
   }
+}
+
+// the 1-D factors of one Gauss point: f[order][b1] at fg[3*order + b1], g[order][b2] at fg[9 + 3*order + b2]
+MAF_HD void load_fg(const double* Fg, double fg[18]) {
+#pragma unroll
+  for (int q = 0; q < 9; ++q) { const dbl2 v2 = ld2(Fg + 2 * q); fg[2 * q] = v2.x; fg[2 * q + 1] = v2.y; }
 }
 
 // Mesh-column block: trial channels N1,N2 (per mesh dof j, stored) and N11,N22,N12 (expanded on the fly from the
@@ -589,90 +656,152 @@ MAF_HD void block_accumulate(const double* __restrict__ A0, int asize, int ald, 
 template <int NR>
 MAF_HD void block_accumulate_mesh(const double* __restrict__ A0, int asize, int ald, int boff,
                                   const double* __restrict__ Phi, const double* __restrict__ FG,
-                                  const double* __restrict__ G, int c0, int a2, int i, int j, bool qterm,
-                                  double acc[3][9]) {
+                                  const double* __restrict__ G, int c0, int a, int i, int j, bool qterm,
+                                  double acc[9]) {
 #pragma unroll
-  for (int a1 = 0; a1 < 3; ++a1)
-#pragma unroll
-    for (int b = 0; b < 9; ++b) acc[a1][b] = 0.0;
+  for (int b = 0; b < 9; ++b) acc[b] = 0.0;
+  const int pa = phi_a(a);
+#pragma unroll 1
   for (int gp = 0; gp < 9; ++gp) {
     const double* Ag = A0 + (size_t)asize * gp;
-    const double* Pg = Phi + PHI_GP * gp;
+    const double* Pg = Phi + PHI_GP * gp + pa;
     const double* Gg = G + G_STRIDE * gp;
-    double u[3][5];
-#pragma unroll
-    for (int a1 = 0; a1 < 3; ++a1)
-#pragma unroll
-      for (int d = 0; d < 5; ++d) u[a1][d] = 0.0;
+    double u[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int c = 0; c < NR; ++c) {
-      const dbl2 p01 = ld2(Pg + PHI_C * (c0 + c) + 4 * a2);
-      const double p2 = Pg[PHI_C * (c0 + c) + 4 * a2 + 2];
+      const double p = Pg[PHI_C * (c0 + c)];
       const double* row = Ag + c * ald;
       const dbl2 a01 = ld2(row);          // (j, N1), (j, N2)
       const dbl2 b01 = ld2(row + boff);   // b-directions 11, 22
       const double b2v = row[boff + 2];   // b-direction 12
-      const double av[5] = {a01.x, a01.y, b01.x, b01.y, b2v};
-#pragma unroll
-      for (int d = 0; d < 5; ++d) {
-        u[0][d] += p01.x * av[d];
-        u[1][d] += p01.y * av[d];
-        u[2][d] += p2 * av[d];
-      }
+      u[0] += p * a01.x; u[1] += p * a01.y; u[2] += p * b01.x; u[3] += p * b01.y; u[4] += p * b2v;
     }
     const double nj = Gg[G_N + j];
-    double t[3] = {0.0, 0.0, 0.0};
-    if (qterm) {
-      const double u0 = Gg[G_UP + j], u1 = Gg[G_UP + 3 + j];
-      const dbl2 P1 = ld2(Pg + PHI_C * CH_N1 + 4 * a2), P2 = ld2(Pg + PHI_C * CH_N2 + 4 * a2);
-      t[0] = u0 * P1.x + u1 * P2.x;
-      t[1] = u0 * P1.y + u1 * P2.y;
-      t[2] = u0 * Pg[PHI_C * CH_N1 + 4 * a2 + 2] + u1 * Pg[PHI_C * CH_N2 + 4 * a2 + 2];
-    }
+    double t = 0.0;
+    if (qterm) t = Gg[G_UP + j] * Pg[PHI_C * CH_N1] + Gg[G_UP + 3 + j] * Pg[PHI_C * CH_N2];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double qw = qterm ? Gg[G_QW + 3 * k + i] : 0.0;
-#pragma unroll
-      for (int a1 = 0; a1 < 3; ++a1) u[a1][2 + k] = nj * u[a1][2 + k] - qw * t[a1];
-    }
-    // f[order][b1] at Fg[3*order + b1], g[order][b2] at Fg[9 + 3*order + b2]
-    const double* Fg = FG + FG_STRIDE * gp;
+    for (int k = 0; k < 3; ++k) u[2 + k] = nj * u[2 + k] - (qterm ? Gg[G_QW + 3 * k + i] : 0.0) * t;
     double fg[18];
+    load_fg(FG + FG_STRIDE * gp, fg);
 #pragma unroll
-    for (int q = 0; q < 9; ++q) { const dbl2 v2 = ld2(Fg + 2 * q); fg[2 * q] = v2.x; fg[2 * q + 1] = v2.y; }
+    for (int b2 = 0; b2 < 3; ++b2) {
+      const double g0 = fg[9 + b2], g1 = fg[12 + b2], g2 = fg[15 + b2];
+      const double t1 = u[0] * g0 + u[4] * g1;   // multiplies f1[b1]   (N1, N12)
+      const double t0 = u[1] * g1 + u[3] * g2;   // multiplies f0[b1]   (N2, N22)
+      const double t2 = u[2] * g0;               // multiplies f2[b1]   (N11)
 #pragma unroll
-    for (int a1 = 0; a1 < 3; ++a1)
-#pragma unroll
-      for (int b2 = 0; b2 < 3; ++b2) {
-        const double g0 = fg[9 + b2], g1 = fg[12 + b2], g2 = fg[15 + b2];
-        const double t1 = u[a1][0] * g0 + u[a1][4] * g1;   // multiplies f1[b1]   (N1, N12)
-        const double t0 = u[a1][1] * g1 + u[a1][3] * g2;   // multiplies f0[b1]   (N2, N22)
-        const double t2 = u[a1][2] * g0;                   // multiplies f2[b1]   (N11)
-#pragma unroll
-        for (int b1 = 0; b1 < 3; ++b1) {   // three separate multiply-adds (each contracts to one DFMA)
-          double s = acc[a1][b1 + 3 * b2];
-          s += fg[3 + b1] * t1;
-          s += fg[b1] * t0;
-          s += fg[6 + b1] * t2;
-          acc[a1][b1 + 3 * b2] = s;
-        }
+      for (int b1 = 0; b1 < 3; ++b1) {           // three separate multiply-adds (each contracts to one DFMA)
+        double sacc = acc[b1 + 3 * b2];
+        sacc += fg[3 + b1] * t1;
+        sacc += fg[b1] * t0;
+        sacc += fg[6 + b1] * t2;
+        acc[b1 + 3 * b2] = sacc;
       }
+    }
   }
 }
 
-// destination of the 27 outputs of a task
+// Fused ALEVB block: K[(a,vm_i),(b,vm_j)] and K[(a,v_i),(b,vm_j)] together. The v rows differ from the vm rows only
+// by the lambda / viscous terms, which touch the rows N1,N2 and the columns N1,N2: the bending + moment tangent
+// (5 rows x 5 channels, the expensive part) is contracted once and shared; Am holds dS_m (6 rows incl. N),
+// Av holds the 2 x 2 corner difference d(S_v - S_m).
+MAF_HD void block_accumulate_fused(const double* __restrict__ Am, int ald_m, int boff, const double* __restrict__ Av,
+                                   int ald_v, int asize, const double* __restrict__ Phi,
+                                   const double* __restrict__ FG, const double* __restrict__ G, int a, int i, int j,
+                                   double acc_mm[9], double acc_vm[9]) {
+  // acc_vm accumulates the DIFFERENCE to the vm rows: only the first-derivative channels N1, N2 differ
+  //   u_v - u_m = (corner difference) - (row N of the vm equations, -J pm n_i)
+#pragma unroll
+  for (int b = 0; b < 9; ++b) { acc_mm[b] = 0.0; acc_vm[b] = 0.0; }
+  const int pa = phi_a(a);
+#pragma unroll 1
+  for (int gp = 0; gp < 9; ++gp) {
+    const double* Pg = Phi + PHI_GP * gp + pa;
+    const double* Gg = G + G_STRIDE * gp;
+    const double* Amg = Am + (size_t)asize * gp;
+    const double* Avg = Av + (size_t)asize * gp;
+    double u[5];
+    const double pN = Pg[PHI_C * CH_N];
+    const dbl2 n01 = ld2(Amg);
+    u[0] = pN * n01.x; u[1] = pN * n01.y; u[2] = 0.0; u[3] = 0.0; u[4] = 0.0;
+    const double p1 = Pg[PHI_C * CH_N1], p2 = Pg[PHI_C * CH_N2];
+    const dbl2 c1 = ld2(Avg), c2 = ld2(Avg + ald_v);
+    double dl0 = -u[0], dl1 = -u[1];
+    dl0 += p1 * c1.x; dl1 += p1 * c1.y;
+    dl0 += p2 * c2.x; dl1 += p2 * c2.y;
+#pragma unroll
+    for (int c = 1; c < 6; ++c) {
+      const double p = Pg[PHI_C * c];
+      const double* row = Amg + c * ald_m;
+      const dbl2 a01 = ld2(row);
+      const dbl2 b01 = ld2(row + boff);
+      const double b2v = row[boff + 2];
+      u[0] += p * a01.x; u[1] += p * a01.y; u[2] += p * b01.x; u[3] += p * b01.y; u[4] += p * b2v;
+    }
+    const double nj = Gg[G_N + j];
+    const double t = Gg[G_UP + j] * p1 + Gg[G_UP + 3 + j] * p2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u[2 + k] = nj * u[2 + k] - Gg[G_QW + 3 * k + i] * t;
+    double fg[18];
+    load_fg(FG + FG_STRIDE * gp, fg);
+#pragma unroll
+    for (int b2 = 0; b2 < 3; ++b2) {
+      const double g0 = fg[9 + b2], g1 = fg[12 + b2], g2 = fg[15 + b2];
+      const double t1 = u[0] * g0 + u[4] * g1;
+      const double t0 = u[1] * g1 + u[3] * g2;
+      const double t2 = u[2] * g0;
+      const double e1 = dl0 * g0, e0 = dl1 * g1;
+#pragma unroll
+      for (int b1 = 0; b1 < 3; ++b1) {
+        double sacc = acc_mm[b1 + 3 * b2], dacc = acc_vm[b1 + 3 * b2];
+        sacc += fg[3 + b1] * t1;
+        sacc += fg[b1] * t0;
+        sacc += fg[6 + b1] * t2;
+        dacc += fg[3 + b1] * e1;
+        dacc += fg[b1] * e0;
+        acc_mm[b1 + 3 * b2] = sacc; acc_vm[b1 + 3 * b2] = dacc;
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 9; ++b) acc_vm[b] += acc_mm[b];
+}
+
+// destination of the outputs of a task
 struct KSink {
   double* nzval;            // atomics path: global CSC values
   double* kel;              // deterministic path: this element's staging rows [a*9+b][nij], or NULL
-  const int16_t* task_ij;   // deterministic path: per task, column of its (row dof, col dof) class in a staging row
   int nij;
 };
 
-MAF_HD void phase_tangent_task(const Config& cfg, int task_id, const double* fr, const double* sm,
+// scatter of the 9 entries of row (a, I) in the columns (b, J), b = 0..8
+MAF_HD void scatter_row(const Config& cfg, const double* fr, const KSink& sink, int a, int I, int J,
+                        const double acc[9]) {
+  if (sink.kel) {  // deterministic path: stage, a gather kernel sums in ascending element order
+    double* dst = sink.kel + (size_t)(9 * a) * sink.nij + cfg.ij_of[8 * I + J];
+#pragma unroll
+    for (int b = 0; b < 9; ++b) dst[(size_t)b * sink.nij] = acc[b];
+    return;
+  }
+  // atomics path: K_gl[LM[i], LM[j]] += K_el[i, j] for active rows and columns (FiniteElement.jl:129-136)
+  const int32_t* si = reinterpret_cast<const int32_t*>(fr + cfg.o_int);
+  const unsigned m = (unsigned)si[I_MASK + a];
+  if (!((m >> I) & 1u)) return;   // rows of inactive dofs are discarded (FiniteElement.jl:107,129)
+  const long long* col = reinterpret_cast<const long long*>(fr + cfg.o_slot) + J;
+  const uint8_t* po8 = reinterpret_cast<const uint8_t*>(fr + cfg.o_po) + 72 * a + J;
+  double* dst = sink.nzval + popc8(m & cfg.rowmask[J] & ((1u << I) - 1u));
+#pragma unroll
+  for (int b = 0; b < 9; ++b) {
+    const long long cb = col[8 * b];   // negative: columns exist only for active dofs (FiniteElement.jl:111)
+    if (cb >= 0) atomic_add(dst + (cb + (long long)po8[8 * b]), acc[b]);
+  }
+}
+
+MAF_HD void phase_tangent_task(const Config& cfg, const Block bk, int t, const double* fr, const double* sm,
                                const KSink& sink) {
-  const Task tk = cfg.tasks[task_id];
-  const Block bk = cfg.blocks[tk.blk];
-  const int f = bk.f, g = bk.g, i = tk.i, j = tk.j, a2 = tk.a2;
+  const int f = bk.f, g = bk.g;
+  const int a = t % 9, ij = t / 9;
+  const int j = cfg.pcomp[g][ij % cfg.npc[g]], i = cfg.pcomp[f][ij / cfg.npc[g]];
   const double* A0 = sm + cfg.o_A + a_index(cfg, f, i, bk.c0, g, j, bk.d0);
   const double* Phi = fr + cfg.o_phi;
   const int ald = cfg.ald[f];
@@ -680,60 +809,51 @@ MAF_HD void phase_tangent_task(const Config& cfg, int task_id, const double* fr,
   const int boff = bk.mesh ? cfg.bcol[f] - (cfg.coloff[f][g] + j * cfg.cnc[f][g]) : 0;
   const double* G = sm + cfg.o_G;
   const double* FG = fr + cfg.o_FG;
-  double acc[3][9];
-  switch (bk.kind) {
-    case 0: block_accumulate<1, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
-    case 1: block_accumulate<1, 2>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
-    case 2: block_accumulate<1, 3>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
-    case 3: block_accumulate<2, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
-    case 4: block_accumulate<2, 2>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a2, acc); break;
-    case 5: block_accumulate_mesh<3>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a2, i, j, bk.qterm, acc); break;
-    case 6: block_accumulate_mesh<5>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a2, i, j, bk.qterm, acc); break;
-    default: block_accumulate_mesh<6>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a2, i, j, bk.qterm, acc); break;
+  const int I = cfg.fdof[f][i], J = cfg.fdof[g][j];
+  double acc[9];
+  if (bk.fused) {
+    double acc_v[9];
+    const double* Av = sm + cfg.o_A + a_index(cfg, F_V, i, CH_N1, g, j, CH_N1);
+    block_accumulate_fused(A0, ald, boff, Av, cfg.ald[F_V], cfg.asize, Phi, FG, G, a, i, j, acc, acc_v);
+    scatter_row(cfg, fr, sink, a, cfg.fdof[F_V][i], J, acc_v);
+    scatter_row(cfg, fr, sink, a, I, J, acc);
+    return;
   }
-  const int32_t* si = reinterpret_cast<const int32_t*>(fr + cfg.o_int);
+  switch (bk.kind) {
+    case 0: block_accumulate<1, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a, acc); break;
+    case 1: block_accumulate<1, 2>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a, acc); break;
+    case 2: block_accumulate<1, 3>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a, acc); break;
+    case 3: block_accumulate<2, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a, acc); break;
+    case 4: block_accumulate<2, 2>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a, acc); break;
+    case 5: block_accumulate_mesh<3>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a, i, j, bk.qterm, acc); break;
+    case 6: block_accumulate_mesh<5>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a, i, j, bk.qterm, acc); break;
+    default: block_accumulate_mesh<6>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a, i, j, bk.qterm, acc); break;
+  }
   if (bk.db) {  // Dohrmann-Bochev stabilisation matrix (state independent), FiniteElement.jl:323-327
     const double* tdb = fr + cfg.o_tdb;
 #pragma unroll
-    for (int a1 = 0; a1 < 3; ++a1)
-#pragma unroll
-      for (int b = 0; b < 9; ++b) acc[a1][b] += cfg.dbscale * tdb[9 * (a1 + 3 * a2) + b];
+    for (int b = 0; b < 9; ++b) acc[b] += cfg.dbscale * tdb[9 * a + b];
   }
-  if (sink.kel) {  // deterministic path: stage, a gather kernel sums in ascending element order
-    double* dst = sink.kel + sink.task_ij[task_id];
-#pragma unroll
-    for (int a1 = 0; a1 < 3; ++a1)
-#pragma unroll
-      for (int b = 0; b < 9; ++b) dst[(size_t)(9 * (a1 + 3 * a2) + b) * sink.nij] = acc[a1][b];
-    return;
-  }
-  // atomics path: K_gl[LM[i], LM[j]] += K_el[i, j] for active rows and columns (FiniteElement.jl:129-136)
-  const int I = cfg.fdof[f][i], J = cfg.fdof[g][j];
-  const unsigned rmask = cfg.rowmask[J] & ((1u << I) - 1u);
-  const int32_t* cprel = reinterpret_cast<const int32_t*>(fr + cfg.o_slot) + J;
-  const uint8_t* po8 = reinterpret_cast<const uint8_t*>(fr + cfg.o_po) + 72 * 3 * a2 + J;   // row of node (0, a2)
-  double* nzb = sink.nzval + *reinterpret_cast<const int64_t*>(fr + cfg.o_base);
-  int off[3];
-#pragma unroll
-  for (int a1 = 0; a1 < 3; ++a1) {
-    const unsigned m = (unsigned)si[I_MASK + a1 + 3 * a2];
-    // rows of inactive dofs are discarded: an offset that can never be reached marks them
-    off[a1] = ((m >> I) & 1u) ? popc8(m & rmask) : SLOT_NONE;
-  }
-#pragma unroll
-  for (int b = 0; b < 9; ++b) {
-    const int rel = cprel[8 * b];
-    if (rel == SLOT_NONE) continue;
-#pragma unroll
-    for (int a1 = 0; a1 < 3; ++a1)
-      if (off[a1] != SLOT_NONE) atomic_add(nzb + (off[a1] + rel + (int)po8[72 * a1 + 8 * b]), acc[a1][b]);
-  }
+  scatter_row(cfg, fr, sink, a, I, J, acc);
 }
 
+#if defined(MAF_PHASE_TIMING) && defined(__CUDACC__)
+__device__ unsigned long long g_chunk_cycles[MAF_MAX_CHUNKS];   // profiling build: cycles per tangent chunk
+#endif
 MAF_HD void phase_tangent(int tid, const Config& cfg, const double* fr, const double* sm, const KSink& sink) {
+  const int warp = tid >> 5, lane = tid & 31, nwarps = cfg.nthreads >> 5;
   for (int r = 0; r < cfg.task_rounds; ++r) {
-    const int id = cfg.task_slot[r * cfg.nthreads + tid];
-    if (id >= 0) phase_tangent_task(cfg, id, fr, sm, sink);
+    const int id = cfg.chunk_slot[r * nwarps + warp];
+    if (id < 0) continue;
+    const Chunk ch = cfg.chunks[id];
+#if defined(MAF_PHASE_TIMING) && defined(__CUDA_ARCH__)
+    const long long t0 = clock64();
+#endif
+    if (lane < ch.count) phase_tangent_task(cfg, cfg.blocks[ch.blk], ch.first + lane, fr, sm, sink);
+#if defined(MAF_PHASE_TIMING) && defined(__CUDA_ARCH__)
+    __syncwarp();
+    if (lane == 0) atomicAdd(&g_chunk_cycles[id], (unsigned long long)(clock64() - t0));
+#endif
   }
 }
 

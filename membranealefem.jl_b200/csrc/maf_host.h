@@ -23,6 +23,8 @@ struct HostModel {
   int ndf = 0, num1el = 0, num2el = 0, nuel1 = 0, nuel2 = 0, motion = 0, scenario = 0, pattern_mode = 0;
   std::vector<int32_t> IX0, ID0, uel1, uel2;
   std::vector<double> line1, line2, edge1, edge2, tdb, utab;
+  std::vector<int64_t> nodecol;      // column pointers per (node, dof) (Tables)
+  std::vector<int32_t> nodemask32;
   std::vector<int32_t> b_elems, b_offs, b_bdry, b_type;
   std::vector<double> b_val;
   int n_neu = 0;
@@ -97,6 +99,15 @@ inline void build_host_model(HostModel& M, const maf_mesh_desc* d, const maf_par
                p->pattern_mode == MAF_PATTERN_SYM, nthreads);
   build_symbolic(M.sym, M.numel, M.numnp, M.ndf, M.nmdf, M.IX0.data(), M.ID0.data(), M.cfg.rowmask);
   build_tdb(M.nuel1, M.nuel2, M.line1.data(), M.line2.data(), d->xi, M.tdb);
+  // column pointers by node, so that the element gather needs no ID -> colptr indirection
+  M.nodecol.assign((size_t)8 * M.numnp, -1);
+  M.nodemask32.assign(M.sym.nodemask.begin(), M.sym.nodemask.end());
+  for (int64_t n = 0; n < M.numnp; ++n) {
+    for (int J = 0; J < M.ndf; ++J) {
+      const int32_t eq = M.ID0[(size_t)M.ndf * n + J];
+      if (eq >= 0) M.nodecol[8 * n + J] = M.sym.colptr[eq];
+    }
+  }
   // basis blocks per unique element (skipped when the knot vectors are so irregular that the table would be large)
   if ((int64_t)M.nuel1 * M.nuel2 <= 4096) {
     M.utab.assign((size_t)M.nuel1 * M.nuel2 * BASIS_DOUBLES, 0.0);
@@ -134,7 +145,7 @@ inline Tables host_tables(const HostModel& M) {
   T.IX = M.IX0.data(); T.ID = M.ID0.data(); T.nodemask = M.sym.nodemask.data();
   T.uel1 = M.uel1.data(); T.uel2 = M.uel2.data(); T.line1 = M.line1.data(); T.line2 = M.line2.data();
   T.tdb = M.tdb.data(); T.colptr = M.sym.colptr.data(); T.elpair = M.sym.elpair.data();
-  T.pairoff = M.sym.pairoff.data(); T.eq0 = M.sym.eq0.data(); T.utab = M.utab.empty() ? nullptr : M.utab.data(); T.numnp = M.numnp; T.numel = M.numel; T.num1el = M.num1el; T.nuel1 = M.nuel1;
+  T.pairoff = M.sym.pairoff.data(); T.eq0 = M.sym.eq0.data(); T.nodecol = M.nodecol.data(); T.nodemask32 = M.nodemask32.data(); T.utab = M.utab.empty() ? nullptr : M.utab.data(); T.numnp = M.numnp; T.numel = M.numel; T.num1el = M.num1el; T.nuel1 = M.nuel1;
   return T;
 }
 inline BoundaryTables host_boundary_tables(const HostModel& M) {
@@ -152,7 +163,7 @@ inline double neumann_value(int ntype, double nval, double time, double bend_tm)
 // host tables of the deterministic path
 struct GatherHost {
   std::vector<int32_t> pair_node;
-  std::vector<int16_t> ij_of, task_ij;
+  std::vector<int16_t> ij_of;
   uint8_t class_I[64], class_J[64];
   int nij = 0, sym_fill = 0;
 };
@@ -161,28 +172,18 @@ inline void build_gather_host(const HostModel& M, GatherHost& GH) {
   GH.pair_node.resize(S.npairs);
   for (int64_t B = 0; B < M.numnp; ++B)
     for (int64_t p = S.nbr_ptr[B]; p < S.nbr_ptr[B + 1]; ++p) GH.pair_node[p] = (int32_t)B;
-  // (I,J) classes = distinct (row dof, col dof) pairs that own tangent tasks, in destination order (J, then I)
-  bool has[8][8] = {};
-  for (int t = 0; t < M.cfg.ntasks; ++t) {
-    const Task& tk = M.cfg.tasks[t];
-    const Block& bk = M.cfg.blocks[tk.blk];
-    has[M.cfg.fdof[bk.f][tk.i]][M.cfg.fdof[bk.g][tk.j]] = true;
-  }
+  // (I,J) classes = distinct (row dof, col dof) pairs that own tangent tasks, in destination order (J, then I):
+  // numbered by build_config (Config::ij_of)
   GH.ij_of.assign(64, -1);
   GH.nij = 0;
   for (int J = 0; J < 8; ++J)
     for (int I = 0; I < 8; ++I)
-      if (has[I][J]) {
+      if (M.cfg.ij_of[8 * I + J] >= 0) {
+        if (M.cfg.ij_of[8 * I + J] != GH.nij) throw std::runtime_error("internal: class numbering");
         GH.class_I[GH.nij] = (uint8_t)I;
         GH.class_J[GH.nij] = (uint8_t)J;
         GH.ij_of[8 * I + J] = (int16_t)GH.nij++;
       }
-  GH.task_ij.assign(M.cfg.ntasks, -1);
-  for (int t = 0; t < M.cfg.ntasks; ++t) {
-    const Task& tk = M.cfg.tasks[t];
-    const Block& bk = M.cfg.blocks[tk.blk];
-    GH.task_ij[t] = GH.ij_of[8 * M.cfg.fdof[bk.f][tk.i] + M.cfg.fdof[bk.g][tk.j]];
-  }
   GH.sym_fill = M.pattern_mode == MAF_PATTERN_SYM ? 1 : 0;
 }
 inline void fill_gather_tables(const GatherHost& GH, GatherTables& G) {

@@ -22,6 +22,7 @@ CASES = {
     "lag_bend_4x3": (maf.LAG, maf.F_BEND, 4, 3, 1.0, {}, {"bend_tm": 2.0, "bend_mf": 0.5}, "deformed"),
     "eul_bend_3x4": (maf.EUL, maf.F_BEND, 3, 4, 1.0, {}, {"bend_tm": 2.0, "bend_mf": 0.5}, "deformed"),
     "alev_bend_4x4_pn": (maf.ALEV, maf.F_BEND, 4, 4, 1.0, {"pn": 0.3}, {"bend_tm": 0.4, "bend_mf": 0.5}, "deformed"),
+    "alevb_bend_pn_4x3": (maf.ALEVB, maf.F_BEND, 4, 3, 1.0, {"pn": 0.25}, {"bend_tm": 0.4, "bend_mf": 0.5}, "deformed"),
     "lag_bend_pn_3x3": (maf.LAG, maf.F_BEND, 3, 3, 1.0, {"pn": -0.4}, {"bend_tm": 2.0, "bend_mf": 0.5}, "deformed"),
 }
 SMALL = list(CASES)

@@ -17,29 +17,38 @@ static void run_area(const HostModel& M, const Tables& T, const double* xms, con
                      double* nzval, double* kel, double* rel, const GatherHost* GH, int64_t e0, int64_t e1) {
   const Config& cfg = M.cfg;
   const int nt = cfg.nthreads;
+  if (nt != MAF_NT) throw std::runtime_error("the element phases are written for MAF_NT threads");
   std::vector<double> smem_all(cfg.smem_doubles);
   std::vector<int32_t> order;
   build_element_order(M.num1el, e0, e1, order);
   const int nfront = cfg.front_doubles;
-  double* sm = smem_all.data() + 2 * nfront;
-  // same software pipeline as the kernel: the "last warp" (32 lanes) gathers the next element into the other buffer
+  int32_t* ids0 = reinterpret_cast<int32_t*>(smem_all.data() + 2 * nfront);
+  double* sm = smem_all.data() + 2 * nfront + 2 * MAF_IDS_DOUBLES;
+  // same software pipeline as the kernel (the asynchronous copies complete at once here)
   std::fill(smem_all.begin(), smem_all.end(), std::nan(""));  // any read of an unwritten slot poisons the result
-  if (!order.empty())
-    for (int t = 0; t < nt; ++t) phase_gather(t, nt, cfg, T, order[0], xms, cps, smem_all.data());
+  for (int t = 0; t < nt; ++t) gather_init(t, cfg, smem_all.data());
+  for (int t = 0; t < nt; ++t) gather_init(t, cfg, smem_all.data() + nfront);
+  if (!order.empty()) {
+    for (int t = 0; t < nt; ++t) gather_ids_async(t, T, order[0], ids0);
+    for (int t = 0; t < nt; ++t) gather_data_async(t, cfg, T, ids0, xms, cps, smem_all.data());
+    if (order.size() > 1)
+      for (int t = 0; t < nt; ++t) gather_ids_async(t, T, order[1], ids0 + MAF_IDS_INTS);
+  }
   int cur = 0;
   for (size_t k = 0; k < order.size(); ++k, cur ^= 1) {
     const int64_t el = order[k];
     const double* fr = smem_all.data() + cur * nfront;
     std::fill(sm, smem_all.data() + smem_all.size(), std::nan(""));
+    if (k + 1 < order.size()) {
+      for (int t = 0; t < nt; ++t)
+        gather_data_async(t, cfg, T, ids0 + (cur ^ 1) * MAF_IDS_INTS, xms, cps, smem_all.data() + (cur ^ 1) * nfront);
+      if (k + 2 < order.size())
+        for (int t = 0; t < nt; ++t) gather_ids_async(t, T, order[k + 2], ids0 + cur * MAF_IDS_INTS);
+    }
     for (int t = 0; t < nt; ++t) phase_interp(t, nt, cfg, fr, sm);
     for (int t = 0; t < nt; ++t) phase_gauss<MOTION>(t, cfg, dt, fr, sm);
-    if (k + 1 < order.size()) {
-      double* nf = smem_all.data() + (cur ^ 1) * nfront;
-      std::fill(nf, nf + nfront, std::nan(""));
-      for (int l = 0; l < 32; ++l) phase_gather(l, 32, cfg, T, order[k + 1], xms, cps, nf);
-    }
-    KSink sink{nzval, nullptr, nullptr, 0};
-    if (kel) sink = KSink{nullptr, kel + (size_t)81 * GH->nij * (el - e0), GH->task_ij.data(), GH->nij};
+    KSink sink{nzval, nullptr, 0};
+    if (kel) sink = KSink{nullptr, kel + (size_t)81 * GH->nij * (el - e0), GH->nij};
     for (int t = 0; t < nt; ++t) phase_residual(t, nt, cfg, fr, sm, r, rel ? rel + 72 * (el - e0) : nullptr);
     for (int t = 0; t < nt; ++t) phase_tangent(t, cfg, fr, sm, sink);
   }
@@ -75,6 +84,18 @@ void emu_info(void* h, int64_t* o) {
   const Config& c = ((emu_model*)h)->M.cfg;
   o[0] = c.asize; o[1] = c.smem_doubles; o[2] = c.ntasks; o[3] = c.nitems; o[4] = c.item_rounds;
   o[5] = c.task_rounds; o[6] = c.nblocks;
+}
+
+// tangent schedule: per chunk [f, g, kind, fused, first, count], then chunk_slot[task_rounds * nwarps]
+int emu_chunks(void* h, int32_t* chunks6, int32_t* slots) {
+  const Config& c = ((emu_model*)h)->M.cfg;
+  for (int k = 0; k < c.nchunks; ++k) {
+    const Block& b = c.blocks[c.chunks[k].blk];
+    const int32_t v[6] = {b.f, b.g, b.kind, b.fused, c.chunks[k].first, c.chunks[k].count};
+    for (int q = 0; q < 6; ++q) chunks6[6 * k + q] = v[q];
+  }
+  for (int q = 0; q < c.task_rounds * (c.nthreads / 32); ++q) slots[q] = c.chunk_slot[q];
+  return c.nchunks;
 }
 
 int emu_assemble(void* h, const double* xms, const double* cps, double time, double dt, double bend_tm, int mode,

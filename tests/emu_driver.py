@@ -56,6 +56,14 @@ class Emu:
         return dict(zip(["asize", "smem_doubles", "ntasks", "nitems", "item_rounds", "task_rounds", "nblocks"],
                         o.tolist()))
 
+    def chunks(self):
+        """Tangent schedule: ([(f, g, kind, fused, first, count)], slots[round][warp])."""
+        c6 = np.zeros(6 * 48, dtype=np.int32)
+        sl = np.full(16 * 8, -1, dtype=np.int32)
+        n = lib().emu_chunks(self.h, c6.ctypes.data_as(C.POINTER(C.c_int32)), sl.ctypes.data_as(C.POINTER(C.c_int32)))
+        rounds = self.info()["task_rounds"]
+        return [tuple(c6[6 * k:6 * k + 6].tolist()) for k in range(n)], sl[:rounds * 4].reshape(rounds, 4).tolist()
+
     def pattern(self):
         colptr = np.empty(self.mesh.nmdf + 1, dtype=np.int64)
         rowval = np.empty(self.nnz, dtype=np.int64)

@@ -27,3 +27,15 @@ for _ in range(a.reps):
     asm.sync()
     print(asm.timings())
 print(asm.kernel_info(), "numel", mesh.numel, "nnz", asm.nnz)
+
+# profiling builds only (-DMAF_PHASE_TIMING): where the warps of a CTA spend their cycles
+import ctypes  # noqa: E402
+L = maf.pkg.capi.load_library()
+if hasattr(L, "maf_debug_phase_cycles"):
+    buf = (ctypes.c_ulonglong * 96)()
+    if L.maf_debug_phase_cycles(buf, 96) == 0:
+        names = ["wait0", "interp", "wait1", "gauss", "wait2", "gather", "res+tan", "-"]
+        tot = sum(buf[q] for q in range(8))
+        for w in range(4):
+            print("warp", w, " ".join(f"{n}={100.0 * buf[8 * w + q] / tot:5.1f}%" for q, n in enumerate(names[:7])))
+        print("chunk cycles (% of one warp's total):", [round(100.0 * buf[32 + q] / tot, 1) for q in range(48) if buf[32 + q]])
