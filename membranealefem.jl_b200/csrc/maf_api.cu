@@ -24,7 +24,7 @@
 using namespace maf;
 
 #ifndef MAF_MIN_CTAS
-#define MAF_MIN_CTAS 3  // resident CTAs per SM the register allocation is capped for
+#define MAF_MIN_CTAS 3  // resident CTAs per SM the register allocation is capped for (168 registers per thread)
 #endif
 
 static_assert(sizeof(Config) <= 4000, "Config must fit the kernel parameter space");
@@ -55,8 +55,14 @@ __device__ __forceinline__ long long maf_clock() {   // not to be moved across b
 #define MAF_TICK(k)
 #endif
 
+// LAG / STATIC evaluate a smaller Gauss-point program (no mesh equations): they fit 128 registers, one more CTA per SM
+#ifndef MAF_MIN_CTAS_LAG
+#define MAF_MIN_CTAS_LAG 4
+#endif
+constexpr int min_ctas(int motion) { return (motion == M_LAG || motion == M_STATIC) ? MAF_MIN_CTAS_LAG : MAF_MIN_CTAS; }
+
 template <int MOTION>
-__global__ void __launch_bounds__(MAF_NT, MAF_MIN_CTAS)
+__global__ void __launch_bounds__(MAF_NT, min_ctas(MOTION))
 area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __restrict__ xms,
             const double* __restrict__ cps, double dt, double* __restrict__ r_gl, double* __restrict__ nzval,
             const StageSink st, const int32_t* __restrict__ order, int64_t e0, int64_t e1) {

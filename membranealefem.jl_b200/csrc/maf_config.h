@@ -24,9 +24,10 @@ inline int kind_of(int nr, int nc) {
 #ifndef MAF_TASK_FIXED
 #define MAF_TASK_FIXED 37
 #endif
-inline int kind_cost(int kind, bool fused) {
+inline int kind_cost(int kind, bool fused, bool tr) {
   static const int tab[8][2] = {{1, 1}, {1, 2}, {1, 3}, {2, 1}, {2, 2}, {3, 5}, {5, 5}, {6, 5}};
   if (fused) return MAF_TASK_FIXED + 107;
+  if (tr) return MAF_TASK_FIXED + tab[kind][0] * tab[kind][1] + 9 * tab[kind][0];
   if (tab[kind][1] == 5) return MAF_TASK_FIXED + 5 * tab[kind][0] + 8 + 42;   // sum-factorised mesh-column blocks
   return MAF_TASK_FIXED + tab[kind][0] * tab[kind][1] + 9 * tab[kind][1];
 }
@@ -127,7 +128,7 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
     const bool q = is_mesh(b) && (b.f == F_V || (b.f == F_M && motion == M_ALEVB));
     cfg.blocks[k] = Block{(int8_t)b.f, (int8_t)b.g, (int8_t)b.c0, (int8_t)b.nr, (int8_t)b.d0, (int8_t)b.nc,
                           (int8_t)kind_of(b.nr, b.nc), (int8_t)b.db, (int8_t)(is_mesh(b) ? 1 : 0), (int8_t)(q ? 1 : 0),
-                          (int8_t)b.notask, (int8_t)b.fused};
+                          (int8_t)b.notask, (int8_t)b.fused, (int8_t)((!is_mesh(b) && b.nr < b.nc) ? 1 : 0)};
   }
   // present components of every field; (row dof, col dof) classes of the deterministic staging rows,
   // in destination order (J, then I)
@@ -159,7 +160,7 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
     cfg.ntasks += nt;
     const int parts = (nt + 31) / 32, per = (nt + parts - 1) / parts;
     for (int first = 0; first < nt; first += per)
-      chs.push_back(Ch{k, first, std::min(per, nt - first), kind_cost(b.kind, b.fused != 0)});
+      chs.push_back(Ch{k, first, std::min(per, nt - first), kind_cost(b.kind, b.fused != 0, b.tr != 0)});
   }
   if ((int)chs.size() > MAF_MAX_CHUNKS) throw std::runtime_error("chunk table overflow");
 
@@ -299,7 +300,36 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   cfg.o_G = o; o += 9 * G_STRIDE;
   o += o & 1;
   cfg.o_A = o; o += 9 * cfg.asize;
+  cfg.o_ctr = o; o += 2;
   cfg.smem_doubles = 2 * cfg.front_doubles + 2 * MAF_IDS_DOUBLES + o;
+  // flattened task descriptors (need the final storage layout and rowmask)
+  for (int k = 0; k < cfg.nblocks; ++k) {
+    const Block& b = cfg.blocks[k];
+    TaskDesc& d = cfg.td[k];
+    std::memset(&d, 0, sizeof(d));
+    const int f = b.f, g = b.g;
+    d.a0 = (int16_t)a_index(cfg, f, 0, b.c0, g, 0, b.d0);
+    d.si = (int16_t)(cfg.rnc[f] * cfg.ald[f]);
+    d.sj = (int16_t)cfg.cnc[f][g];
+    d.ald = (int16_t)cfg.ald[f];
+    d.boff0 = (int16_t)(b.mesh ? cfg.bcol[f] - cfg.coloff[f][g] : 0);
+    if (b.fused) {
+      d.av0 = (int16_t)a_index(cfg, F_V, 0, CH_N1, g, 0, CH_N1);
+      d.svi = (int16_t)(cfg.rnc[F_V] * cfg.ald[F_V]);
+      d.svj = (int16_t)cfg.cnc[F_V][g];
+      d.aldv = (int16_t)cfg.ald[F_V];
+    }
+    d.c0 = (uint8_t)b.c0; d.d0 = (uint8_t)b.d0; d.kind = (uint8_t)b.kind; d.npcg = (uint8_t)cfg.npc[g];
+    d.mesh = (uint8_t)b.mesh; d.qterm = (uint8_t)b.qterm; d.fused = (uint8_t)b.fused; d.tr = (uint8_t)b.tr; d.db = (uint8_t)b.db;
+    for (int q = 0; q < 3; ++q) {
+      d.ic[q] = q < cfg.npc[f] ? (uint8_t)cfg.pcomp[f][q] : 0;
+      d.jc[q] = q < cfg.npc[g] ? (uint8_t)cfg.pcomp[g][q] : 0;
+      d.I[q] = (q < cfg.ncomp[f] && cfg.fdof[f][q] >= 0) ? (uint8_t)cfg.fdof[f][q] : 0;
+      d.J[q] = (q < cfg.ncomp[g] && cfg.fdof[g][q] >= 0) ? (uint8_t)cfg.fdof[g][q] : 0;
+      d.Iv[q] = cfg.fdof[F_V][q] >= 0 ? (uint8_t)cfg.fdof[F_V][q] : 0;
+      d.rm[q] = (q < cfg.ncomp[g] && cfg.fdof[g][q] >= 0) ? cfg.rowmask[cfg.fdof[g][q]] : 0;
+    }
+  }
   // everything that is read with 16-byte loads must sit on an even double offset
   bool ok = !(cfg.o_A & 1) && !(cfg.o_phi & 1) && !(cfg.o_FG & 1) && !(cfg.asize & 1) &&
             !(cfg.front_doubles & 1) && !(cfg.o_po & 1);

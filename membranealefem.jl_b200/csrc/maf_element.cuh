@@ -35,12 +35,28 @@ struct Block {      // one (row field, col field) tangent block type
   int8_t qterm;     // mesh block whose rows carry the moment term -Q_k Gamma^mu_k (v rows; vm rows for ALEVB)
   int8_t notask;    // storage only: its entries are consumed by the fused block (ALEVB corner differences)
   int8_t fused;     // (vm, mesh) block that also produces the (v, mesh) block (shared bending tangent, ALEVB)
+  int8_t tr;        // fewer row than column channels: the task owns a COLUMN (b, J) and contracts the columns first
 };
 // A tangent task = the 9 entries K_el[(a,I),(b,J)], b = 0..8, of one (block, row comp i, col comp j, row node a),
-// accumulated over the 9 Gauss points in registers. Tasks of a block are numbered t = a + 9 (jj + npc[g] ii) over
+// accumulated over the 9 Gauss points in registers (transposed blocks: the 9 entries a = 0..8 of one column node
+// b, which costs nr nc + 9 nr instead of nr nc + 9 nc operations per Gauss point). Tasks of a block are numbered t = a + 9 (jj + npc[g] ii) over
 // the PRESENT components; a chunk is <= 32 consecutive tasks of one block, executed by the lanes of one warp.
 struct Chunk {
   uint8_t blk, first, count, pad;
+};
+// Everything a tangent task needs to know about its block, flattened so that the task set-up is one uniform
+// constant load instead of a chain of dependent table look-ups (which cost more than the arithmetic of the
+// short blocks). Indexed by component: comp i = ic[ii], j = jc[jj].
+struct alignas(8) TaskDesc {
+  int16_t a0, si, sj;       // A offset of (i, c0; j, d0) = a0 + i si + j sj   (doubles, relative to o_A)
+  int16_t ald;              // row stride of the row field
+  int16_t boff0;            // mesh blocks: offset from the (j, N1) entry to the b-direction columns = boff0 - j sj
+  int16_t av0, svi, svj, aldv;   // fused block: the corner difference of the v rows
+  uint8_t c0, d0, kind, npcg;
+  uint8_t mesh, qterm, fused, tr, db;
+  uint8_t ic[3], jc[3];     // present components
+  uint8_t I[3], J[3], Iv[3];  // dof of row comp i, column comp j, v-row comp i (by component)
+  uint8_t rm[3];            // rowmask of the column dof J (by component)
 };
 struct Item {       // phase-G work item of one Gauss point
   uint8_t type, gp, gamma, j;
@@ -71,6 +87,7 @@ struct Config {
   int ntasks;                     // total number of tangent tasks (diagnostics)
   int nchunks;
   Chunk chunks[MAF_MAX_CHUNKS];
+  TaskDesc td[MAF_MAX_BLOCKS];
   int npc[NFIELD];                // present components per field and their indices
   int8_t pcomp[NFIELD][3];
   int8_t ij_of[64];               // deterministic path: staging column of the (row dof I, col dof J) class, -1 none
@@ -86,7 +103,7 @@ struct Config {
   Material mat;
   double dbscale;                 // adb / zv
   // shared-memory layout (offsets in doubles from the element's block)
-  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_G, o_A, o_int, o_slot, o_po, o_FG, o_tdb, front_doubles, smem_doubles;
+  int o_x, o_cv, o_cm, o_cl, o_cp, o_w, o_phi, o_E, o_S, o_G, o_A, o_int, o_slot, o_po, o_FG, o_tdb, o_ctr, front_doubles, smem_doubles;
 };
 
 // interpolated Gauss-point inputs E[gp][.]
@@ -260,6 +277,7 @@ MAF_HD void gather_ids_async(int tid, const Tables& T, int64_t el, int32_t* ids)
 // Scatter map of the element, looked up once:
 //   slot(a, I; b, J) = col[8 b + J] + po[(9 a + b) * 8 + J] + rank(I | a, J)
 // col = column pointer of (b, J) (negative for a Dirichlet column), po = the pairoff row of the node pair (a, b).
+// (Folding col + po into one int32 table per element was measured: the extra pass costs what it saves.)
 #define MAF_GATHER_ITEMS 333
 MAF_HD void gather_data_async(int tid, const Config& cfg, const Tables& T, const int32_t* ids, const double* xms,
                               const double* cps, double* fr /* front block of the element */) {
@@ -311,6 +329,7 @@ MAF_HD void phase_interp(int tid, int nt, const Config& cfg, const double* fr, d
     dbl2* Az = reinterpret_cast<dbl2*>(sm + cfg.o_A);
     const dbl2 z = {0.0, 0.0};
     for (int k = tid; k < 9 * cfg.asize / 2; k += nt) Az[k] = z;
+    if (tid == 0) *reinterpret_cast<int*>(sm + cfg.o_ctr) = 0;   // chunk queue of the tangent phase
   }
   for (int k = tid; k < 9 * 35; k += nt) {
     const int gp = k / 35, q = k % 35;
@@ -643,6 +662,40 @@ MAF_HD void block_accumulate(const double* __restrict__ A0, int asize, int ald, 
   }
 }
 
+// transposed form for blocks with fewer row than column channels: v[c] = sum_d A[(i,c)][(j,d)] Phi^d_b, then
+// K[a] += sum_c Phi^c_a v[c] for the 9 row nodes a
+template <int NR, int NC>
+MAF_HD void block_accumulate_tr(const double* __restrict__ A0, int asize, int ald, const double* __restrict__ Phi,
+                                int c0, int d0, int b, double acc[9]) {
+#pragma unroll
+  for (int a = 0; a < 9; ++a) acc[a] = 0.0;
+  const int pb = phi_a(b);
+#pragma unroll 1
+  for (int gp = 0; gp < 9; ++gp) {
+    const double* Ag = A0 + (size_t)asize * gp;
+    const double* Pg = Phi + PHI_GP * gp;
+    double v[NR];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) v[c] = 0.0;
+#pragma unroll
+    for (int d = 0; d < NC; ++d) {
+      const double q = Pg[PHI_C * (d0 + d) + pb];
+#pragma unroll
+      for (int c = 0; c < NR; ++c) v[c] += q * Ag[c * ald + d];
+    }
+#pragma unroll
+    for (int c = 0; c < NR; ++c)
+#pragma unroll
+      for (int a2 = 0; a2 < 3; ++a2) {
+        const dbl2 p01 = ld2(Pg + PHI_C * (c0 + c) + 4 * a2);
+        const double p2 = Pg[PHI_C * (c0 + c) + 4 * a2 + 2];
+        acc[3 * a2] += v[c] * p01.x;
+        acc[3 * a2 + 1] += v[c] * p01.y;
+        acc[3 * a2 + 2] += v[c] * p2;
+      }
+  }
+}
+
 // the 1-D factors of one Gauss point: f[order][b1] at fg[3*order + b1], g[order][b2] at fg[9 + 3*order + b2]
 MAF_HD void load_fg(const double* Fg, double fg[18]) {
 #pragma unroll
@@ -775,7 +828,7 @@ struct KSink {
 };
 
 // scatter of the 9 entries of row (a, I) in the columns (b, J), b = 0..8
-MAF_HD void scatter_row(const Config& cfg, const double* fr, const KSink& sink, int a, int I, int J,
+MAF_HD void scatter_row(const Config& cfg, const double* fr, const KSink& sink, int a, int I, int J, unsigned rm,
                         const double acc[9]) {
   if (sink.kel) {  // deterministic path: stage, a gather kernel sums in ascending element order
     double* dst = sink.kel + (size_t)(9 * a) * sink.nij + cfg.ij_of[8 * I + J];
@@ -789,7 +842,7 @@ MAF_HD void scatter_row(const Config& cfg, const double* fr, const KSink& sink, 
   if (!((m >> I) & 1u)) return;   // rows of inactive dofs are discarded (FiniteElement.jl:107,129)
   const long long* col = reinterpret_cast<const long long*>(fr + cfg.o_slot) + J;
   const uint8_t* po8 = reinterpret_cast<const uint8_t*>(fr + cfg.o_po) + 72 * a + J;
-  double* dst = sink.nzval + popc8(m & cfg.rowmask[J] & ((1u << I) - 1u));
+  double* dst = sink.nzval + popc8(m & rm & ((1u << I) - 1u));
 #pragma unroll
   for (int b = 0; b < 9; ++b) {
     const long long cb = col[8 * b];   // negative: columns exist only for active dofs (FiniteElement.jl:111)
@@ -797,64 +850,107 @@ MAF_HD void scatter_row(const Config& cfg, const double* fr, const KSink& sink, 
   }
 }
 
-MAF_HD void phase_tangent_task(const Config& cfg, const Block bk, int t, const double* fr, const double* sm,
-                               const KSink& sink) {
-  const int f = bk.f, g = bk.g;
-  const int a = t % 9, ij = t / 9;
-  const int j = cfg.pcomp[g][ij % cfg.npc[g]], i = cfg.pcomp[f][ij / cfg.npc[g]];
-  const double* A0 = sm + cfg.o_A + a_index(cfg, f, i, bk.c0, g, j, bk.d0);
-  const double* Phi = fr + cfg.o_phi;
-  const int ald = cfg.ald[f];
-  // offset from the (j, N1) entry of a row to its b-direction columns
-  const int boff = bk.mesh ? cfg.bcol[f] - (cfg.coloff[f][g] + j * cfg.cnc[f][g]) : 0;
-  const double* G = sm + cfg.o_G;
-  const double* FG = fr + cfg.o_FG;
-  const int I = cfg.fdof[f][i], J = cfg.fdof[g][j];
-  double acc[9];
-  if (bk.fused) {
-    double acc_v[9];
-    const double* Av = sm + cfg.o_A + a_index(cfg, F_V, i, CH_N1, g, j, CH_N1);
-    block_accumulate_fused(A0, ald, boff, Av, cfg.ald[F_V], cfg.asize, Phi, FG, G, a, i, j, acc, acc_v);
-    scatter_row(cfg, fr, sink, a, cfg.fdof[F_V][i], J, acc_v);
-    scatter_row(cfg, fr, sink, a, I, J, acc);
+// scatter of the 9 entries of column (b, J) in the rows (a, I), a = 0..8 (transposed blocks)
+MAF_HD void scatter_col(const Config& cfg, const double* fr, const KSink& sink, int b, int I, int J, unsigned rm,
+                        const double acc[9]) {
+  if (sink.kel) {
+    double* dst = sink.kel + (size_t)b * sink.nij + cfg.ij_of[8 * I + J];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) dst[(size_t)(9 * a) * sink.nij] = acc[a];
     return;
   }
-  switch (bk.kind) {
-    case 0: block_accumulate<1, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a, acc); break;
-    case 1: block_accumulate<1, 2>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a, acc); break;
-    case 2: block_accumulate<1, 3>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a, acc); break;
-    case 3: block_accumulate<2, 1>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a, acc); break;
-    case 4: block_accumulate<2, 2>(A0, cfg.asize, ald, Phi, bk.c0, bk.d0, a, acc); break;
-    case 5: block_accumulate_mesh<3>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a, i, j, bk.qterm, acc); break;
-    case 6: block_accumulate_mesh<5>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a, i, j, bk.qterm, acc); break;
-    default: block_accumulate_mesh<6>(A0, cfg.asize, ald, boff, Phi, FG, G, bk.c0, a, i, j, bk.qterm, acc); break;
+  const long long cb = *(reinterpret_cast<const long long*>(fr + cfg.o_slot) + 8 * b + J);
+  if (cb < 0) return;   // columns exist only for active dofs (FiniteElement.jl:111)
+  const int32_t* si = reinterpret_cast<const int32_t*>(fr + cfg.o_int);
+  const uint8_t* po8 = reinterpret_cast<const uint8_t*>(fr + cfg.o_po) + 8 * b + J;
+  double* dst = sink.nzval + cb;
+  const unsigned low = (1u << I) - 1u;
+#pragma unroll
+  for (int a = 0; a < 9; ++a) {
+    const unsigned m = (unsigned)si[I_MASK + a];
+    if ((m >> I) & 1u) atomic_add(dst + ((int)po8[72 * a] + popc8(m & rm & low)), acc[a]);
   }
-  if (bk.db) {  // Dohrmann-Bochev stabilisation matrix (state independent), FiniteElement.jl:323-327
+}
+
+MAF_HD void phase_tangent_task(const Config& cfg, const TaskDesc& d, int t, const double* fr, const double* sm,
+                               const KSink& sink) {
+  const int a = t % 9, ij = t / 9;
+  const int jj = ij % d.npcg, ii = ij / d.npcg;
+  const int i = d.ic[ii], j = d.jc[jj];
+  const double* A0 = sm + cfg.o_A + (d.a0 + i * d.si + j * d.sj);
+  const double* Phi = fr + cfg.o_phi;
+  const int ald = d.ald;
+  const int boff = d.boff0 - j * d.sj;   // offset from the (j, N1) entry of a row to its b-direction columns
+  const double* G = sm + cfg.o_G;
+  const double* FG = fr + cfg.o_FG;
+  const int I = d.I[i], J = d.J[j];
+  const unsigned rm = d.rm[j];
+  double acc[9];
+  if (d.fused) {
+    double acc_v[9];
+    const double* Av = sm + cfg.o_A + (d.av0 + i * d.svi + j * d.svj);
+    block_accumulate_fused(A0, ald, boff, Av, d.aldv, cfg.asize, Phi, FG, G, a, i, j, acc, acc_v);
+    scatter_row(cfg, fr, sink, a, d.Iv[i], J, rm, acc_v);
+    scatter_row(cfg, fr, sink, a, I, J, rm, acc);
+    return;
+  }
+  if (d.tr) {   // here `a` is the column node b
+    if (d.kind == 1) block_accumulate_tr<1, 2>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc);
+    else block_accumulate_tr<1, 3>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc);
+    scatter_col(cfg, fr, sink, a, I, J, rm, acc);
+    return;
+  }
+  switch (d.kind) {
+    case 0: block_accumulate<1, 1>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc); break;
+    case 3: block_accumulate<2, 1>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc); break;
+    case 4: block_accumulate<2, 2>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc); break;
+    case 5: block_accumulate_mesh<3>(A0, cfg.asize, ald, boff, Phi, FG, G, d.c0, a, i, j, d.qterm, acc); break;
+    case 6: block_accumulate_mesh<5>(A0, cfg.asize, ald, boff, Phi, FG, G, d.c0, a, i, j, d.qterm, acc); break;
+    default: block_accumulate_mesh<6>(A0, cfg.asize, ald, boff, Phi, FG, G, d.c0, a, i, j, d.qterm, acc); break;
+  }
+  if (d.db) {  // Dohrmann-Bochev stabilisation matrix (state independent), FiniteElement.jl:323-327
     const double* tdb = fr + cfg.o_tdb;
 #pragma unroll
     for (int b = 0; b < 9; ++b) acc[b] += cfg.dbscale * tdb[9 * a + b];
   }
-  scatter_row(cfg, fr, sink, a, I, J, acc);
+  scatter_row(cfg, fr, sink, a, I, J, rm, acc);
 }
 
 #if defined(MAF_PHASE_TIMING) && defined(__CUDACC__)
 __device__ unsigned long long g_chunk_cycles[MAF_MAX_CHUNKS];   // profiling build: cycles per tangent chunk
 #endif
-MAF_HD void phase_tangent(int tid, const Config& cfg, const double* fr, const double* sm, const KSink& sink) {
-  const int warp = tid >> 5, lane = tid & 31, nwarps = cfg.nthreads >> 5;
-  for (int r = 0; r < cfg.task_rounds; ++r) {
-    const int id = cfg.chunk_slot[r * nwarps + warp];
-    if (id < 0) continue;
+MAF_HD void phase_tangent(int tid, const Config& cfg, const double* fr, double* sm, const KSink& sink) {
+  const int warp = tid >> 5, lane = tid & 31;
+#if defined(__CUDA_ARCH__) && defined(MAF_DYNAMIC_SCHED)   // variant, measured 4 % slower than the static plan
+  // the warps pull the chunks (sorted by decreasing cost) from a queue in shared memory: whichever warp is free takes
+  // the next one, so the phase balances itself whatever the other phases and the other CTAs of the SM are doing
+  (void)warp;
+  int* ctr = reinterpret_cast<int*>(sm + cfg.o_ctr);
+  for (;;) {
+    int id = 0;
+    if (lane == 0) id = atomicAdd(ctr, 1);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (id >= cfg.nchunks) break;
     const Chunk ch = cfg.chunks[id];
-#if defined(MAF_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#if defined(MAF_PHASE_TIMING)
     const long long t0 = clock64();
 #endif
-    if (lane < ch.count) phase_tangent_task(cfg, cfg.blocks[ch.blk], ch.first + lane, fr, sm, sink);
-#if defined(MAF_PHASE_TIMING) && defined(__CUDA_ARCH__)
+    if (lane < ch.count) phase_tangent_task(cfg, cfg.td[ch.blk], ch.first + lane, fr, sm, sink);
+#if defined(MAF_PHASE_TIMING)
     __syncwarp();
     if (lane == 0) atomicAdd(&g_chunk_cycles[id], (unsigned long long)(clock64() - t0));
 #endif
   }
+#else
+  // static longest-processing-time plan (maf_config.h)
+  const int nwarps = cfg.nthreads >> 5;
+  for (int r = 0; r < cfg.task_rounds; ++r) {
+    const int id = cfg.chunk_slot[r * nwarps + warp];
+    if (id < 0) continue;
+    const Chunk ch = cfg.chunks[id];
+    if (lane < ch.count) phase_tangent_task(cfg, cfg.td[ch.blk], ch.first + lane, fr, sm, sink);
+  }
+#endif
 }
 
 }  // namespace maf
