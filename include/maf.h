@@ -147,6 +147,30 @@ int maf_kernel_info(maf_handle* h, int64_t* out5);
 int maf_set_element_range(maf_handle* h, int64_t el_first, int64_t el_last);
 int maf_range_info(maf_handle* h, int64_t* out8);
 
+/* ---- Device-resident state: the glue of time_step! between two calls of calc_r_K ----------------
+ * With these the state never returns to the host inside a time step; per Newton iteration only r / nzval come back
+ * and du goes in. maf_assemble also leaves the state it was given resident.
+ *
+ * maf_state_set / maf_state_get   copy xms (numnp x 3) and cps (numnp x ndf), column-major Float64, to / from the
+ *                                 device (either pointer of _get may be NULL).
+ * maf_state_update(du, dt)        dcps[ID_inv] = du; cps += dcps; update_xms!(xms, dcps, dt)
+ *                                 (FiniteElement.jl:41-46, 408-423). du: nmdf values. Bit-identical to the host loop
+ *                                 (the product dt * dcps is rounded before the sum, no FMA).
+ * maf_state_predict(dt)           update_xms!(xms, cps, dt), the predictor of run_analysis (Analysis.jl:70).
+ * maf_assemble_resident(...)      maf_assemble on the resident state (no host-to-device copy of the state). */
+int maf_state_set(maf_handle* h, const double* xms, const double* cps);
+int maf_state_get(maf_handle* h, double* xms, double* cps);
+int maf_state_update(maf_handle* h, const double* du, double dt);
+int maf_state_predict(maf_handle* h, double dt);
+int maf_assemble_resident(maf_handle* h, double time, double dt, double bend_tm, int scatter_mode, double* r,
+                          double* nzval, double* rnorm2);
+
+/* rv of calc_elem_dof_residuals (FiniteElement.jl:253-330, real parts) of n elements (1-based ids) on the resident
+ * state: rv[27 k + comp + 3 (a - 1)], all rows incl. those of Dirichlet dofs -- what calc_pull_force
+ * (PullForce.jl:61-80) sums over the elements adjacent to the pulled one. Needs a 3-D velocity
+ * (Analysis.jl:48). */
+int maf_elem_v_residuals(maf_handle* h, const int64_t* el_ids, int64_t n, double* rv);
+
 /* Measured FP64 FMA throughput of the device (TFLOP/s): the denominator of the FP64 roofline fraction. */
 int maf_fp64_peak(int device, double* tflops);
 

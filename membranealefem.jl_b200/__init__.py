@@ -14,5 +14,6 @@ from .host.enums import *  # noqa: F401,F403
 from .host.input import prepare_input, synthetic_state
 from .host.mesh import Mesh, get_basis_fns, get_ddN, get_dN, get_gpw, get_N
 from .host import partition
+from .host.pullforce import calc_pull_force, get_adj_maps, get_pull_el_id
 from .host.params import Params, check_params
 from .host.spline import KnotVector

@@ -44,7 +44,8 @@ _lib = None
 EXPORTS = ["maf_create", "maf_destroy", "maf_last_error", "maf_nnz", "maf_pattern", "maf_assemble",
            "maf_assemble_device", "maf_device_buffers", "maf_stream", "maf_sync", "maf_timings", "maf_launch_count",
            "maf_kernel_info", "maf_set_element_range", "maf_range_info", "maf_fp64_peak",
-           "maf_debug_phase_cycles"]
+           "maf_debug_phase_cycles", "maf_state_set", "maf_state_get", "maf_state_update", "maf_state_predict",
+           "maf_assemble_resident", "maf_elem_v_residuals"]
 
 
 def load_library(path=None):
@@ -76,6 +77,12 @@ def load_library(path=None):
     L.maf_set_element_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     L.maf_range_info.argtypes = [C.c_void_p, _I64P]
     L.maf_fp64_peak.argtypes = [C.c_int, _F64P]
+    L.maf_state_set.argtypes = [C.c_void_p, _F64P, _F64P]
+    L.maf_state_get.argtypes = [C.c_void_p, _F64P, _F64P]
+    L.maf_state_update.argtypes = [C.c_void_p, _F64P, C.c_double]
+    L.maf_state_predict.argtypes = [C.c_void_p, C.c_double]
+    L.maf_assemble_resident.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, _F64P, _F64P, _F64P]
+    L.maf_elem_v_residuals.argtypes = [C.c_void_p, _I64P, C.c_int64, _F64P]
     if path == LIB_PATH:
         _lib = L
     return L
@@ -178,6 +185,43 @@ class Assembler:
         self._check(self.L.maf_assemble(self.h, _ptr(xms, C.c_double), _ptr(cps, C.c_double), time, dt, bend_tm,
                                         scatter_mode, _ptr(r, C.c_double), _ptr(nzval, C.c_double), C.byref(rn)))
         return r, nzval, rn.value
+
+    # ---- device-resident state (include/maf.h: maf_state_*) ----
+    def state_set(self, xms, cps):
+        xms = np.asfortranarray(xms, dtype=np.float64)
+        cps = np.asfortranarray(cps, dtype=np.float64)
+        assert xms.shape == (self.mesh.numnp, 3) and cps.shape == (self.mesh.numnp, self.mesh.ndf)
+        self._check(self.L.maf_state_set(self.h, _ptr(xms, C.c_double), _ptr(cps, C.c_double)))
+
+    def state_get(self):
+        xms = np.empty((self.mesh.numnp, 3), order="F")
+        cps = np.empty((self.mesh.numnp, self.mesh.ndf), order="F")
+        self._check(self.L.maf_state_get(self.h, _ptr(xms, C.c_double), _ptr(cps, C.c_double)))
+        return xms, cps
+
+    def state_update(self, du, dt):
+        du = np.ascontiguousarray(du, dtype=np.float64)
+        assert du.shape == (self.nmdf,)
+        self._check(self.L.maf_state_update(self.h, _ptr(du, C.c_double), dt))
+
+    def state_predict(self, dt):
+        self._check(self.L.maf_state_predict(self.h, dt))
+
+    def assemble_resident(self, time, dt, bend_tm=1.0, scatter_mode=SCATTER_ATOMIC, r=None, nzval=None):
+        """maf_assemble_resident: like assemble(), on the state the device already holds."""
+        r = np.empty(self.nmdf) if r is None else r
+        nzval = np.empty(self.nnz) if nzval is None else nzval
+        rn = C.c_double()
+        self._check(self.L.maf_assemble_resident(self.h, time, dt, bend_tm, scatter_mode, _ptr(r, C.c_double),
+                                                 _ptr(nzval, C.c_double), C.byref(rn)))
+        return r, nzval, rn.value
+
+    def elem_v_residuals(self, el_ids):
+        """rv of calc_elem_dof_residuals for the listed elements (1-based) on the resident state: (n, 27)."""
+        el_ids = np.ascontiguousarray(el_ids, dtype=np.int64)
+        rv = np.empty((el_ids.size, 27))
+        self._check(self.L.maf_elem_v_residuals(self.h, _ptr(el_ids, C.c_int64), el_ids.size, _ptr(rv, C.c_double)))
+        return rv
 
     def assemble_device(self, d_xms, d_cps, time, dt, bend_tm=1.0, scatter_mode=SCATTER_ATOMIC, d_r=None,
                         d_nzval=None, d_rnorm2=None, stream=None):

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "maf_host.h"
+#include "maf_state.cuh"
 
 using namespace maf;
 
@@ -191,6 +192,45 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
   if (s == 12345.678) out[0] = s;  // keeps the chains alive without a store in the common case
 }
 
+// residual of the v rows of a few elements, all rows (also those of Dirichlet dofs): the reaction force of the
+// pulled nodes is summed from them (calc_pull_force, PullForce.jl:61-80). One CTA per listed element; stages the
+// element residual [u][a] (u = v0 v1 v2 m0 m1 m2 l p) like the deterministic path.
+template <int MOTION>
+__global__ void __launch_bounds__(MAF_NT, min_ctas(MOTION))
+elem_residual_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __restrict__ xms,
+                     const double* __restrict__ cps, const int32_t* __restrict__ els, int n, double* __restrict__ rel) {
+  extern __shared__ double smem_all[];
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x >= n) return;
+  int32_t* ids = reinterpret_cast<int32_t*>(smem_all + 2 * cfg.front_doubles);
+  double* sm = smem_all + 2 * cfg.front_doubles + 2 * MAF_IDS_DOUBLES;
+  gather_init(tid, cfg, smem_all);
+  gather_ids_async(tid, T, els[blockIdx.x], ids);
+  async_wait_all();
+  __syncthreads();
+  gather_data_async(tid, cfg, T, ids, xms, cps, smem_all);
+  async_wait_all();
+  __syncthreads();
+  phase_interp(tid, MAF_NT, cfg, smem_all, sm);
+  __syncthreads();
+  phase_gauss<MOTION>(tid, cfg, 0.0, smem_all, sm);
+  __syncthreads();
+  phase_residual(tid, MAF_NT, cfg, smem_all, sm, nullptr, rel + 72 * (size_t)blockIdx.x, true);
+}
+
+__global__ void state_update_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __restrict__ du,
+                                    double dt, double* __restrict__ xms, double* __restrict__ cps) {
+  const int64_t n = T.numnp * cfg.ndf;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    state_update_entry(k, cfg, T, du, dt, xms, cps);
+}
+__global__ void state_predict_kernel(const __grid_constant__ Config cfg, const Tables T, double dt,
+                                     double* __restrict__ xms, const double* __restrict__ cps) {
+  const int64_t n = T.numnp * 3;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    state_predict_entry(k, cfg, T, dt, xms, cps);
+}
+
 __global__ void __launch_bounds__(256) rnorm2_partial(const double* __restrict__ r, int64_t n, double* part) {
   __shared__ double s[256];
   double acc = 0.0;
@@ -235,6 +275,8 @@ struct maf_handle {
   int32_t* d_order = nullptr;   // processing order of the elements of [e0, e1)
   int nij = 0;
   double *d_xms = nullptr, *d_cps = nullptr, *d_r = nullptr, *d_nz = nullptr, *d_rn = nullptr, *d_part = nullptr;
+  double* d_du = nullptr;        // Newton update of the resident state
+  bool state_resident = false;   // d_xms / d_cps hold a state (maf_state_set or maf_assemble)
   double *d_kel = nullptr, *d_rel = nullptr;
   size_t kel_elems = 0;
   double *h_pin_in = nullptr, *h_pin_out = nullptr;  // pinned staging for the host-buffer entry point
@@ -286,6 +328,17 @@ static area_fn area_kernel_of(int motion) {
     case M_LAG: return area_kernel<M_LAG>;
     case M_ALEV: return area_kernel<M_ALEV>;
     default: return area_kernel<M_ALEVB>;
+  }
+}
+
+typedef void (*elres_fn)(const Config, const Tables, const double*, const double*, const int32_t*, int, double*);
+static elres_fn elem_residual_kernel_of(int motion) {
+  switch (motion) {
+    case M_STATIC: return elem_residual_kernel<M_STATIC>;
+    case M_EUL: return elem_residual_kernel<M_EUL>;
+    case M_LAG: return elem_residual_kernel<M_LAG>;
+    case M_ALEV: return elem_residual_kernel<M_ALEV>;
+    default: return elem_residual_kernel<M_ALEVB>;
   }
 }
 
@@ -634,17 +687,11 @@ static bool is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
-int maf_assemble(maf_handle* h, const double* xms, const double* cps, double time, double dt, double bend_tm,
-                 int scatter_mode, double* r, double* nzval, double* rnorm2) {
-  MAF_API_BEGIN(h)
-  if (!xms || !cps || !r || !nzval) throw std::runtime_error("null buffer");
-  if (scatter_mode != MAF_SCATTER_ATOMIC && scatter_mode != MAF_SCATTER_DETERMINISTIC)
-    throw std::runtime_error("unknown scatter mode");
+// host state -> the handle's device buffers (asynchronous on the handle's stream)
+static void upload_state(maf_handle* h, const double* xms, const double* cps) {
   const HostModel& M = h->M;
   cudaStream_t s = h->stream;
   const size_t bx = sizeof(double) * 3 * (size_t)M.numnp, bc = sizeof(double) * (size_t)M.ndf * M.numnp;
-  const size_t br = sizeof(double) * (size_t)M.nmdf, bk = sizeof(double) * (size_t)M.sym.nnz;
-  CU(cudaEventRecord(h->ev[0], s));
   // inputs: page-locked caller memory is copied from directly, anything else through a pinned staging buffer
   // (keeps the copy asynchronous and at full PCIe rate)
   const double *hx = xms, *hc = cps;
@@ -661,6 +708,18 @@ int maf_assemble(maf_handle* h, const double* xms, const double* cps, double tim
   }
   CU(cudaMemcpyAsync(h->d_xms, hx, bx, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(h->d_cps, hc, bc, cudaMemcpyHostToDevice, s));
+  h->state_resident = true;
+}
+
+// assembly of the resident state with the results copied into host buffers; ev[0] must have been recorded
+static void assemble_to_host(maf_handle* h, double time, double dt, double bend_tm, int scatter_mode, double* r,
+                             double* nzval, double* rnorm2) {
+  if (!r || !nzval) throw std::runtime_error("null buffer");
+  if (scatter_mode != MAF_SCATTER_ATOMIC && scatter_mode != MAF_SCATTER_DETERMINISTIC)
+    throw std::runtime_error("unknown scatter mode");
+  const HostModel& M = h->M;
+  cudaStream_t s = h->stream;
+  const size_t br = sizeof(double) * (size_t)M.nmdf, bk = sizeof(double) * (size_t)M.sym.nnz;
   const bool full = h->e0 == 0 && h->e1 == M.numel;
   const bool pipelined = scatter_mode == MAF_SCATTER_ATOMIC && full && M.numel >= 32768 && M.num2el >= 16;
   if (!pipelined) {
@@ -718,6 +777,117 @@ int maf_assemble(maf_handle* h, const double* xms, const double* cps, double tim
   CU(cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]));
   CU(cudaEventElapsedTime(&h->ms[4], h->ev[4], h->ev[5]));
   CU(cudaEventElapsedTime(&h->ms[5], h->ev[0], h->ev[5]));
+}
+
+int maf_assemble(maf_handle* h, const double* xms, const double* cps, double time, double dt, double bend_tm,
+                 int scatter_mode, double* r, double* nzval, double* rnorm2) {
+  MAF_API_BEGIN(h)
+  if (!xms || !cps || !r || !nzval) throw std::runtime_error("null buffer");
+  CU(cudaEventRecord(h->ev[0], h->stream));
+  upload_state(h, xms, cps);
+  assemble_to_host(h, time, dt, bend_tm, scatter_mode, r, nzval, rnorm2);
+  MAF_API_END(h)
+}
+
+// ---- device-resident state: xms / cps stay on the device across the Newton iterations ----
+static void require_state(maf_handle* h) {
+  if (!h->state_resident) throw std::runtime_error("no resident state: call maf_state_set (or maf_assemble) first");
+}
+
+int maf_state_set(maf_handle* h, const double* xms, const double* cps) {
+  MAF_API_BEGIN(h)
+  if (!xms || !cps) throw std::runtime_error("null buffer");
+  upload_state(h, xms, cps);
+  CU(cudaStreamSynchronize(h->stream));   // the caller may reuse its buffers
+  MAF_API_END(h)
+}
+
+int maf_state_get(maf_handle* h, double* xms, double* cps) {
+  MAF_API_BEGIN(h)
+  require_state(h);
+  const HostModel& M = h->M;
+  if (xms) CU(cudaMemcpyAsync(xms, h->d_xms, sizeof(double) * 3 * (size_t)M.numnp, cudaMemcpyDeviceToHost, h->stream));
+  if (cps) CU(cudaMemcpyAsync(cps, h->d_cps, sizeof(double) * (size_t)M.ndf * M.numnp, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  MAF_API_END(h)
+}
+
+int maf_state_update(maf_handle* h, const double* du, double dt) {
+  MAF_API_BEGIN(h)
+  require_state(h);
+  if (!du) throw std::runtime_error("null buffer");
+  if (!(dt == dt)) throw std::runtime_error("dt is NaN");
+  const HostModel& M = h->M;
+  if (!h->d_du) h->d_du = dalloc<double>(h, (size_t)M.nmdf);
+  CU(cudaMemcpyAsync(h->d_du, du, sizeof(double) * (size_t)M.nmdf, cudaMemcpyHostToDevice, h->stream));
+  const int grid = (int)std::min<int64_t>((M.numnp * M.ndf + 255) / 256, (int64_t)h->sm_count * 16);
+  state_update_kernel<<<std::max(grid, 1), 256, 0, h->stream>>>(M.cfg, h->T, h->d_du, dt, h->d_xms, h->d_cps);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(cudaStreamSynchronize(h->stream));   // du is the caller's
+  MAF_API_END(h)
+}
+
+int maf_state_predict(maf_handle* h, double dt) {
+  MAF_API_BEGIN(h)
+  require_state(h);
+  if (!(dt == dt)) throw std::runtime_error("dt is NaN");
+  const HostModel& M = h->M;
+  const int grid = (int)std::min<int64_t>((M.numnp * 3 + 255) / 256, (int64_t)h->sm_count * 16);
+  state_predict_kernel<<<std::max(grid, 1), 256, 0, h->stream>>>(M.cfg, h->T, dt, h->d_xms, h->d_cps);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  MAF_API_END(h)
+}
+
+int maf_assemble_resident(maf_handle* h, double time, double dt, double bend_tm, int scatter_mode, double* r,
+                          double* nzval, double* rnorm2) {
+  MAF_API_BEGIN(h)
+  require_state(h);
+  CU(cudaEventRecord(h->ev[0], h->stream));
+  assemble_to_host(h, time, dt, bend_tm, scatter_mode, r, nzval, rnorm2);
+  MAF_API_END(h)
+}
+
+int maf_elem_v_residuals(maf_handle* h, const int64_t* el_ids, int64_t n, double* rv) {
+  MAF_API_BEGIN(h)
+  require_state(h);
+  if (!el_ids || !rv) throw std::runtime_error("null buffer");
+  if (n < 0 || n > 4096) throw std::runtime_error("element count outside 0..4096");
+  const HostModel& M = h->M;
+  if (M.cfg.fdof[F_V][0] < 0 || M.cfg.fdof[F_V][1] < 0 || M.cfg.fdof[F_V][2] < 0)
+    throw std::runtime_error("the pull force needs a 3-D velocity");   // Analysis.jl:48
+  if (n == 0) return 0;
+  std::vector<int32_t> els((size_t)n);
+  for (int64_t k = 0; k < n; ++k) {
+    if (el_ids[k] < 1 || el_ids[k] > M.numel) throw std::runtime_error("element id outside 1..numel");
+    els[(size_t)k] = (int32_t)(el_ids[k] - 1);
+  }
+  int32_t* d_els = nullptr;
+  double* d_rel = nullptr;
+  CU(cudaMalloc(&d_els, sizeof(int32_t) * (size_t)n));
+  CU(cudaMalloc(&d_rel, sizeof(double) * 72 * (size_t)n));
+  std::vector<double> rel((size_t)72 * n);
+  cudaError_t err = cudaMemcpyAsync(d_els, els.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+  if (err == cudaSuccess) {
+    elres_fn kern = elem_residual_kernel_of(M.motion);
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    if (err == cudaSuccess) {
+      kern<<<(int)n, MAF_NT, h->smem_bytes, h->stream>>>(M.cfg, h->T, h->d_xms, h->d_cps, d_els, (int)n, d_rel);
+      h->launches += 1;
+      err = cudaGetLastError();
+    }
+  }
+  if (err == cudaSuccess)
+    err = cudaMemcpyAsync(rel.data(), d_rel, sizeof(double) * 72 * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
+  cudaFree(d_els);
+  cudaFree(d_rel);
+  CU(err);
+  // staged [u][a] (u = v0 v1 v2 ...) -> the reference's rv_el[comp + 3 (a - 1)] (FiniteElement.jl:293-297)
+  for (int64_t k = 0; k < n; ++k)
+    for (int a = 0; a < 9; ++a)
+      for (int i = 0; i < 3; ++i) rv[27 * k + 3 * a + i] = rel[(size_t)72 * k + 9 * i + a];
   MAF_API_END(h)
 }
 

@@ -584,7 +584,8 @@ MAF_HD void phase_gauss(int tid, const Config& cfg, double dt, const double* fr,
 // Phase 3a: element residual r_el and its scatter (FiniteElement.jl:103, 129-131).
 // ---------------------------------------------------------------------------------------------------------
 MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const double* fr, const double* sm, double* r_gl,
-                           double* r_stage /* deterministic path: 72 staged rows of this element, or NULL */) {
+                           double* r_stage /* deterministic path: 72 staged rows of this element, or NULL */,
+                           bool all_rows = false /* also the rows of Dirichlet dofs (pull force) */) {
   const int32_t* si = reinterpret_cast<const int32_t*>(fr + cfg.o_int);
   const double* tdb = fr + cfg.o_tdb;
   for (int k = tid; k < 72; k += nt) {
@@ -593,7 +594,7 @@ MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const double* fr,
     const int i = u < 6 ? u % 3 : 0;
     const int dof = cfg.fdof[f][i];
     const int eq = dof >= 0 ? si[I_EQ + 8 * a + dof] : -1;
-    if (eq < 0) {  // rows of inactive dofs are discarded (FiniteElement.jl:107,129)
+    if (eq < 0 && !(all_rows && dof >= 0)) {  // rows of inactive dofs are discarded (FiniteElement.jl:107,129)
       if (r_stage) r_stage[k] = 0.0;
       continue;
     }

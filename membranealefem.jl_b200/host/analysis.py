@@ -1,7 +1,8 @@
 """Analysis layer around the hot path, mirroring src/analysis/FiniteElement.jl and src/Analysis.jl:
 
   calc_r_K     FiniteElement.jl:75-200  -> the C ABI / CUDA kernels (this is the drop-in)
-  time_step    FiniteElement.jl:11-63   Newton-Raphson loop, host sparse solve
+  time_step    FiniteElement.jl:11-63   Newton-Raphson loop, host sparse solve; resident=True keeps xms / cps on the
+                                        device between the iterations (maf_state_*)
   update_xms   FiniteElement.jl:408-423
   run_analysis Analysis.jl:17-102
 """
@@ -14,8 +15,9 @@ import scipy.sparse.linalg as spla
 
 from ..capi import PATTERN_BLK, SCATTER_ATOMIC, Assembler
 from .enums import F_PULL
-from .mesh import get_m_motion_order
+from .mesh import get_m_motion_order, get_v_order
 from .params import get_dts
+from .pullforce import calc_pull_force, get_adj_maps, get_pull_el_id
 
 
 def _assembler(mesh, p, args):
@@ -63,17 +65,32 @@ def time_step(mesh, xms, cps, time, dt, p, **args):
     timers = args.get("timers")
     log = args.get("log")
     node_of, dof_of = mesh.ID_inv
+    resident = bool(args.get("resident", False))
+    if resident:   # the state lives on the device for the whole step; only r / K come back and du goes in
+        asm = _assembler(mesh, p, args)
+        asm.state_set(xms, cps)
+        colptr, rowval = asm.pattern()
     it = 1
     while it < 15:
         t0 = _time.perf_counter()
-        r_gl, K_gl = calc_r_K(mesh, xms, cps, time, dt, p, **args)
+        if resident:
+            r_gl, nzval, _ = asm.assemble_resident(float(time), float(dt), bend_tm=float(args.get("bend_tm", 1.0)),
+                                                   scatter_mode=args.get("scatter_mode", SCATTER_ATOMIC))
+            K_gl = sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(mesh.nmdf, mesh.nmdf))
+            if args.get("dropzeros", True):
+                K_gl.eliminate_zeros()
+        else:
+            r_gl, K_gl = calc_r_K(mesh, xms, cps, time, dt, p, **args)
         t1 = _time.perf_counter()
         du = -spla.splu(K_gl.tocsc()).solve(r_gl)
         t2 = _time.perf_counter()
-        dcps = np.zeros_like(cps)
-        dcps[node_of - 1, dof_of - 1] = du
-        cps += dcps
-        update_xms(p.motion, xms, dcps, dt, mesh.dofs)
+        if resident:
+            asm.state_update(du, float(dt))
+        else:
+            dcps = np.zeros_like(cps)
+            dcps[node_of - 1, dof_of - 1] = du
+            cps += dcps
+            update_xms(p.motion, xms, dcps, dt, mesh.dofs)
         eps_hist.append(float(np.linalg.norm(du) / mesh.nmdf))
         if timers is not None:
             timers["assembly_s"] = timers.get("assembly_s", 0.0) + (t1 - t0)
@@ -84,6 +101,10 @@ def time_step(mesh, xms, cps, time, dt, p, **args):
         it += 1
         if eps_hist[-1] < p.enr:
             break
+    if resident:   # hand the converged state back (the reference mutates xms / cps in place)
+        x_new, c_new = asm.state_get()
+        xms[...] = x_new
+        cps[...] = c_new
     assert eps_hist[-1] < p.enr, "did not reach Newton--Raphson tolerance"
     return eps_hist
 
@@ -101,6 +122,14 @@ def run_analysis(mesh, xms, cps, p, **args):
             for t_id, t in enumerate(times, start=1):
                 f.write(f"{t_id + args['t0_id']}\t{t}\n")
     histories = []
+    pull = p.scenario == F_PULL
+    if pull:   # pull force local mappings (Analysis.jl:46-56)
+        assert all(get_v_order(mesh.dofs)), "f_pull needs 3-D velocity"
+        adj_el_ids, adj_node_map = get_adj_maps(mesh.num1el, mesh.numel, mesh.IX, p.poly)
+        if out and not args.get("append", False):
+            with open(os.path.join(args["out_path"], "f-pull.txt"), "a") as f:
+                f.write("time\txp\typ\tzp\tfx\tfy\tfz\n")
+    f_pulls = args.get("f_pulls")
     for t_id, dt in enumerate(dts, start=1):
         if log:
             log.write(f"\n-> Time {times[t_id - 1]}\n")
@@ -109,10 +138,15 @@ def run_analysis(mesh, xms, cps, p, **args):
         if out:
             np.savetxt(os.path.join(args["out_path"], f"t{t_id + args['t0_id']}-xms.txt"), xms, delimiter="\t")
             np.savetxt(os.path.join(args["out_path"], f"t{t_id + args['t0_id']}-cps.txt"), cps, delimiter="\t")
-        # calc_pull_force (PullForce.jl:61-80) is SURVEY.md 8(f3) "next": diagnostic only, not on the hot path.
+        if pull and (out or f_pulls is not None):   # pull force calculation (Analysis.jl:80-92)
+            x_pull = xms[mesh.IX[:, get_pull_el_id(mesh.numel) - 1] - 1, :].sum(axis=0) / mesh.IX.shape[0]
+            f_pull = calc_pull_force(mesh, xms, cps, adj_el_ids, adj_node_map, p, **args)
+            if f_pulls is not None:
+                f_pulls.append((float(times[t_id - 1]), x_pull.copy(), f_pull.copy()))
+            if out:
+                with open(os.path.join(args["out_path"], "f-pull.txt"), "a") as f:
+                    f.write("\t".join(repr(float(v)) for v in (times[t_id - 1], *x_pull, *f_pull)) + "\n")
     if log:
         log.write("\nCompleted running analysis...\n\n")
         log.close()
-    if p.scenario == F_PULL and out:
-        pass
     return histories

@@ -350,6 +350,25 @@ class Mesh:
             raise AssertionError(_err())
         return rv, rm, rl, rp
 
+    def calc_pull_force(self, xms, cps, poly=2):
+        """calc_pull_force + get_adj_maps (PullForce.jl:25-80): reaction force on the nodes of the pulled element
+        = sum of rv over the (2 poly + 1)^2 elements around it, restricted to those nodes."""
+        IX = self.IX
+        numel = IX.shape[1]
+        num1el = self.num1el
+        pull_el = int(np.ceil(numel / 2))                               # get_pull_el_id, PullForce.jl:12
+        pull_nodes = list(IX[:, pull_el - 1])
+        rv_pull = np.zeros(27)
+        for i in range(-poly, poly + 1):                                # adj_el_ids, PullForce.jl:36-37
+            for e in range(pull_el + i * num1el - poly, pull_el + i * num1el + poly + 1):
+                adj_nodes = list(IX[:, e - 1])
+                rv_el = self.elem_dof_residuals(e, xms, cps)[0]
+                for ip, n in enumerate(pull_nodes):                     # maps of PullForce.jl:41-49
+                    if n in adj_nodes:
+                        ia = adj_nodes.index(n)
+                        rv_pull[3 * ip:3 * ip + 3] += rv_el[3 * ia:3 * ia + 3]
+        return rv_pull.reshape(9, 3).sum(axis=0)                        # PullForce.jl:79
+
     def calc_r_K(self, xms, cps, time, dt, nthreads=1):
         """Reference calc_r_K (FiniteElement.jl:75-200). Returns (r, scipy CSC K) with the value-dependent
         stored pattern Julia's SparseMatrixCSC would hold (explicit zeros kept, never-nonzero entries absent)."""

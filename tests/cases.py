@@ -35,8 +35,17 @@ DEFAULT_17 = {
 }
 
 
+# meshes with two rings of elements around the pulled one (calc_pull_force, PullForce.jl:36-37)
+PULL = {
+    "lag_pull_7x7": (maf.LAG, maf.F_PULL, 7, 7, 16.0, {}, {"pull_speed": 0.5}, "deformed"),
+    "eul_pull_7x5": (maf.EUL, maf.F_PULL, 7, 5, 16.0, {}, {"pull_speed": 0.5}, "deformed"),
+    "alevb_pull_7x7": (maf.ALEVB, maf.F_PULL, 7, 7, 16.0, {}, {"pull_speed": 0.5}, "deformed"),
+    "alevb_pull_fine_19x19": (maf.ALEVB, maf.F_PULL, 19, 19, 16.0, {}, {"pull_speed": 0.5}, "deformed"),
+}
+
+
 def make_case(name, seed=7):
-    motion, scen, n1, n2, L, extra, args, kind = {**CASES, **DEFAULT_17}[name]
+    motion, scen, n1, n2, L, extra, args, kind = {**CASES, **DEFAULT_17, **PULL}[name]
     p = maf.Params(motion=motion, scenario=scen, num1el=n1, num2el=n2, length=L, output=False, **extra)
     hm = maf.Mesh(p, **args)
     om = orc.Mesh(motion=int(motion), scenario=int(scen), num1el=n1, num2el=n2, length=L, pn=p.pn,

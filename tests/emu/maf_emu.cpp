@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../membranealefem.jl_b200/csrc/maf_host.h"
+#include "../../membranealefem.jl_b200/csrc/maf_state.cuh"
 
 using namespace maf;
 
@@ -54,6 +55,24 @@ static void run_area(const HostModel& M, const Tables& T, const double* xms, con
   }
 }
 
+// elem_residual_kernel (maf_api.cu): staged residual of the listed elements (0-based), rv[27 k + comp + 3 a]
+template <int MOTION>
+static void run_elem_residual(const HostModel& M, const Tables& T, const double* xms, const double* cps, int32_t el,
+                              double* rel) {
+  const Config& cfg = M.cfg;
+  const int nt = cfg.nthreads;
+  std::vector<double> smem_all(cfg.smem_doubles, std::nan(""));
+  int32_t* ids = reinterpret_cast<int32_t*>(smem_all.data() + 2 * cfg.front_doubles);
+  double* sm = smem_all.data() + 2 * cfg.front_doubles + 2 * MAF_IDS_DOUBLES;
+  double* fr = smem_all.data();
+  for (int t = 0; t < nt; ++t) gather_init(t, cfg, fr);
+  for (int t = 0; t < nt; ++t) gather_ids_async(t, T, el, ids);
+  for (int t = 0; t < nt; ++t) gather_data_async(t, cfg, T, ids, xms, cps, fr);
+  for (int t = 0; t < nt; ++t) phase_interp(t, nt, cfg, fr, sm);
+  for (int t = 0; t < nt; ++t) phase_gauss<MOTION>(t, cfg, 0.0, fr, sm);
+  for (int t = 0; t < nt; ++t) phase_residual(t, nt, cfg, fr, sm, nullptr, rel, true);
+}
+
 extern "C" {
 
 const char* emu_last_error() { return g_err.c_str(); }
@@ -96,6 +115,42 @@ int emu_chunks(void* h, int32_t* chunks6, int32_t* slots) {
   }
   for (int q = 0; q < c.task_rounds * (c.nthreads / 32); ++q) slots[q] = c.chunk_slot[q];
   return c.nchunks;
+}
+
+// the resident-state kernels (maf_state.cuh) entry by entry, in place
+void emu_state_update(void* h, const double* du, double dt, double* xms, double* cps) {
+  HostModel& M = ((emu_model*)h)->M;
+  Tables T = host_tables(M);
+  for (int64_t k = 0; k < M.numnp * M.ndf; ++k) state_update_entry(k, M.cfg, T, du, dt, xms, cps);
+}
+void emu_state_predict(void* h, double dt, double* xms, const double* cps) {
+  HostModel& M = ((emu_model*)h)->M;
+  Tables T = host_tables(M);
+  for (int64_t k = 0; k < M.numnp * 3; ++k) state_predict_entry(k, M.cfg, T, dt, xms, cps);
+}
+
+int emu_elem_v_residuals(void* h, const double* xms, const double* cps, const int64_t* el_ids, int64_t n, double* rv) {
+  try {
+    HostModel& M = ((emu_model*)h)->M;
+    Tables T = host_tables(M);
+    for (int64_t k = 0; k < n; ++k) {
+      double rel[72];
+      const int32_t el = (int32_t)(el_ids[k] - 1);
+      switch (M.motion) {
+        case M_STATIC: run_elem_residual<M_STATIC>(M, T, xms, cps, el, rel); break;
+        case M_EUL: run_elem_residual<M_EUL>(M, T, xms, cps, el, rel); break;
+        case M_LAG: run_elem_residual<M_LAG>(M, T, xms, cps, el, rel); break;
+        case M_ALEV: run_elem_residual<M_ALEV>(M, T, xms, cps, el, rel); break;
+        default: run_elem_residual<M_ALEVB>(M, T, xms, cps, el, rel); break;
+      }
+      for (int a = 0; a < 9; ++a)
+        for (int i = 0; i < 3; ++i) rv[27 * k + 3 * a + i] = rel[9 * i + a];
+    }
+    return 0;
+  } catch (std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
 }
 
 int emu_assemble(void* h, const double* xms, const double* cps, double time, double dt, double bend_tm, int mode,

@@ -64,6 +64,29 @@ class Emu:
         rounds = self.info()["task_rounds"]
         return [tuple(c6[6 * k:6 * k + 6].tolist()) for k in range(n)], sl[:rounds * 4].reshape(rounds, 4).tolist()
 
+    def state_update(self, du, dt, xms, cps):
+        dp = C.POINTER(C.c_double)
+        du = np.ascontiguousarray(du, dtype=np.float64)
+        lib().emu_state_update(self.h, du.ctypes.data_as(dp), C.c_double(dt), xms.ctypes.data_as(dp),
+                               cps.ctypes.data_as(dp))
+
+    def state_predict(self, dt, xms, cps):
+        dp = C.POINTER(C.c_double)
+        lib().emu_state_predict(self.h, C.c_double(dt), xms.ctypes.data_as(dp), cps.ctypes.data_as(dp))
+
+    def elem_v_residuals(self, xms, cps, el_ids):
+        dp = C.POINTER(C.c_double)
+        xms = np.asfortranarray(xms, dtype=np.float64)
+        cps = np.asfortranarray(cps, dtype=np.float64)
+        el_ids = np.ascontiguousarray(el_ids, dtype=np.int64)
+        rv = np.empty((el_ids.size, 27))
+        rc = lib().emu_elem_v_residuals(self.h, xms.ctypes.data_as(dp), cps.ctypes.data_as(dp),
+                                        el_ids.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(el_ids.size),
+                                        rv.ctypes.data_as(dp))
+        if rc:
+            raise RuntimeError(lib().emu_last_error().decode())
+        return rv
+
     def pattern(self):
         colptr = np.empty(self.mesh.nmdf + 1, dtype=np.int64)
         rowval = np.empty(self.nnz, dtype=np.int64)
