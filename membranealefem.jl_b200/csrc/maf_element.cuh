@@ -18,6 +18,10 @@
 #define MAF_SMALL_UNROLL 1
 #endif
 constexpr int kSmallUnroll = MAF_SMALL_UNROLL;
+#ifndef MAF_BIG_UNROLL
+#define MAF_BIG_UNROLL 3
+#endif
+constexpr int kBigUnroll = MAF_BIG_UNROLL;   // Gauss-point loop of the mesh-column blocks (measured: LAG +4 %)
 #define MAF_NT 128  // threads per CTA of the area kernel (one element per CTA iteration)
 
 namespace maf {
@@ -715,7 +719,7 @@ MAF_HD void block_accumulate_mesh(const double* __restrict__ A0, int asize, int 
 #pragma unroll
   for (int b = 0; b < 9; ++b) acc[b] = 0.0;
   const int pa = phi_a(a);
-#pragma unroll 1
+#pragma unroll kBigUnroll
   for (int gp = 0; gp < 9; ++gp) {
     const double* Ag = A0 + (size_t)asize * gp;
     const double* Pg = Phi + PHI_GP * gp + pa;
