@@ -22,7 +22,9 @@ constexpr int kSmallUnroll = MAF_SMALL_UNROLL;
 #define MAF_BIG_UNROLL 3
 #endif
 constexpr int kBigUnroll = MAF_BIG_UNROLL;   // Gauss-point loop of the mesh-column blocks (measured: LAG +4 %)
+#ifndef MAF_NT
 #define MAF_NT 128  // threads per CTA of the area kernel (one element per CTA iteration)
+#endif
 
 namespace maf {
 
