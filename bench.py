@@ -293,6 +293,46 @@ def run(a, out_stream):
                        "the host solver needs) inside the timed region (CUDA events on the handle's stream)"}
         err = float(np.abs(hr.numpy() - d_r.cpu().numpy()).max())
         e2e["max_abs_diff_r_vs_device_path"] = err
+    elif not a.no_e2e:
+        # N > 1: every rank uploads the state from pinned host memory, assembles its strip, exchanges the interface
+        # and copies the part of r / nzval it owns (each entry leaves exactly one GPU) to pinned host memory
+        ranges = [t.tolist() for t in allr]
+        own_r, own_k = part.owned_rows(ranges, rank), part.owned_slots(ranges, rank)
+        hx = torch.from_numpy(np.ascontiguousarray(xms.T)).pin_memory()
+        hc = torch.from_numpy(np.ascontiguousarray(cps.T)).pin_memory()
+        hr = torch.empty(own_r.stop - own_r.start, dtype=torch.float64).pin_memory()
+        hk = torch.empty(own_k.stop - own_k.start, dtype=torch.float64).pin_memory()
+        hn = torch.empty(1, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            d_x.copy_(hx, non_blocking=True)
+            d_c.copy_(hc, non_blocking=True)
+            step()
+            hr.copy_(d_r[own_r], non_blocking=True)
+            hk.copy_(d_k[own_k], non_blocking=True)
+            hn.copy_(d_n, non_blocking=True)
+
+        for _ in range(max(1, a.warmup)):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot = float(t.item())
+        nb = torch.tensor([hr.numel() + hk.numel() + 1], dtype=torch.int64, device=dev)
+        dist.all_reduce(nb)
+        e2e = {"value": mesh.numel * a.steps / (tot * 1e-3) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int((3 + mesh.ndf) * mesh.numnp * 8) * world,
+               "d2h_bytes_per_step": int(nb.item()) * 8, "ms_per_step": tot / a.steps,
+               "note": "per rank: H2D xms+cps from pinned host memory, strip assembly, NCCL interface exchange, D2H "
+                       "of the owned rows of r / entries of nzval into pinned host memory (every entry leaves "
+                       "exactly one GPU); CUDA events on the handle's stream, max over ranks",
+               "rnorm2_host": float(hn.item())}
 
     if rank != 0:
         if world > 1:

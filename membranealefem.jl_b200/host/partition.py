@@ -62,6 +62,13 @@ def owned_rows(ranges, rank):
     return slice(lo, ranges[rank][1])
 
 
+def owned_slots(ranges, rank):
+    """Entries of nzval this rank hands to the host: its range minus what the lower neighbour already delivers
+    (after the interface exchange both neighbours hold the complete sums of the overlap)."""
+    lo = ranges[rank][2] - 1 if rank == 0 else max(ranges[rank][2] - 1, ranges[rank - 1][3])
+    return slice(lo, ranges[rank][3])
+
+
 class InterfaceExchange:
     """Sums the interface rows of r and entries of nzval with the neighbouring strips and all-reduces |r|^2."""
 

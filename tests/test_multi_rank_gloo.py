@@ -102,3 +102,5 @@ def test_partition_arithmetic():
                                                        (2, slice(180, 200), slice(1800, 2000))]
     assert part.owned_rows(ranges, 0) == slice(0, 100) and part.owned_rows(ranges, 1) == slice(100, 200)
     assert part.owned_rows(ranges, 2) == slice(200, 300)
+    assert part.owned_slots(ranges, 0) == slice(0, 1000) and part.owned_slots(ranges, 1) == slice(1000, 2000)
+    assert part.owned_slots(ranges, 2) == slice(2000, 3000)
