@@ -245,7 +245,11 @@ MAF_HD void async_copy8(void* sdst, const void* gsrc) {
 }
 MAF_HD void async_copy16(void* sdst, const void* gsrc) {
 #if defined(__CUDA_ARCH__)
+#if defined(MAF_COPY16_CA)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+#else   // bypass L1 (the basis blocks are the bulk of the gathered bytes); measured equal to .ca
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+#endif
 #else
   memcpy(sdst, gsrc, 16);
 #endif
