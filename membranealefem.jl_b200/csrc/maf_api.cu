@@ -2,7 +2,7 @@
 //
 // Kernels (all FP64 CUDA-core work; the per-element products are 9 x <=6 x <=6 contractions, far too small and too
 // irregular for tcgen05 tiles, and FP64 has no tensor-core advantage on this part -- see DESIGN.md):
-//   area_kernel<MOTION>    persistent CTAs, one area element per CTA iteration: gather -> interpolate ->
+//   area_kernel<MOTION, STAGED>  persistent CTAs, one area element per CTA iteration: gather -> interpolate ->
 //                          Gauss-point tangent (forward-mode dual numbers) -> residual + factored tangent
 //                          contraction in registers -> scatter (FP64 RED atomics, or staging for the
 //                          deterministic path)
@@ -62,7 +62,9 @@ __device__ __forceinline__ long long maf_clock() {   // not to be moved across b
 #endif
 constexpr int min_ctas(int motion) { return (motion == M_LAG || motion == M_STATIC) ? MAF_MIN_CTAS_LAG : MAF_MIN_CTAS; }
 
-template <int MOTION>
+// STAGED = deterministic path (staging rows instead of atomics): a separate instantiation, so that each kernel
+// carries one copy of the tangent phase (instruction-cache footprint)
+template <int MOTION, bool STAGED>
 __global__ void __launch_bounds__(MAF_NT, min_ctas(MOTION))
 area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __restrict__ xms,
             const double* __restrict__ cps, double dt, double* __restrict__ r_gl, double* __restrict__ nzval,
@@ -122,7 +124,7 @@ area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __
     __syncthreads();
     MAF_TICK(4)
     MAF_TICK(5)
-    if (st.kel == nullptr) {
+    if (!STAGED) {
       phase_residual(tid, MAF_NT, cfg, fr, sm, r_gl, nullptr);
       KSink sink{nzval, nullptr, 0};
       phase_tangent(tid, cfg, fr, sm, sink);
@@ -322,14 +324,17 @@ template <class Tp> static Tp* dalloc(maf_handle* h, size_t n) {
 
 typedef void (*area_fn)(const Config, const Tables, const double*, const double*, double, double*, double*,
                         const StageSink, const int32_t*, int64_t, int64_t);
-static area_fn area_kernel_of(int motion) {
+template <bool STAGED> static area_fn area_kernel_sel(int motion) {
   switch (motion) {
-    case M_STATIC: return area_kernel<M_STATIC>;
-    case M_EUL: return area_kernel<M_EUL>;
-    case M_LAG: return area_kernel<M_LAG>;
-    case M_ALEV: return area_kernel<M_ALEV>;
-    default: return area_kernel<M_ALEVB>;
+    case M_STATIC: return area_kernel<M_STATIC, STAGED>;
+    case M_EUL: return area_kernel<M_EUL, STAGED>;
+    case M_LAG: return area_kernel<M_LAG, STAGED>;
+    case M_ALEV: return area_kernel<M_ALEV, STAGED>;
+    default: return area_kernel<M_ALEVB, STAGED>;
   }
+}
+static area_fn area_kernel_of(int motion, bool staged = false) {
+  return staged ? area_kernel_sel<true>(motion) : area_kernel_sel<false>(motion);
 }
 
 typedef void (*elres_fn)(const Config, const Tables, const double*, const double*, const int32_t*, int, double*);
@@ -468,7 +473,7 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
   if (!d_nz) d_nz = h->d_nz;
   if (mode != MAF_SCATTER_ATOMIC && mode != MAF_SCATTER_DETERMINISTIC) throw std::runtime_error("unknown scatter mode");
   if (!(dt == dt) || !(time == time)) throw std::runtime_error("time / dt is NaN");
-  area_fn kern = area_kernel_of(M.motion);
+  area_fn kern = area_kernel_of(M.motion, mode == MAF_SCATTER_DETERMINISTIC);
   const int64_t ne = h->e1 - h->e0;
   const int grid = (int)std::min<int64_t>(std::max<int64_t>(ne, 1), (int64_t)h->grid);
   (void)timed;
@@ -626,8 +631,11 @@ int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* pa
     area_fn kern = area_kernel_of(M.motion);
     if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
       throw std::runtime_error("element needs more shared memory than the device offers");
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (int staged = 0; staged < 2; ++staged) {
+      area_fn kq = area_kernel_of(M.motion, staged != 0);
+      CU(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+      CU(cudaFuncSetAttribute(kq, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     int nb = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, MAF_NT, h->smem_bytes));
     if (nb < 1) throw std::runtime_error("area kernel does not fit on an SM");

@@ -164,7 +164,7 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   }
   if ((int)chs.size() > MAF_MAX_CHUNKS) throw std::runtime_error("chunk table overflow");
 
-  // Gauss-point work items: GEO_A (6 per gp) when the mesh moves, GEO_B (1 per gp), LIN (1 per gp)
+  // Gauss-point work items: GEO_A (6 per gp) when the mesh moves, GEO_B (3 per gp: one per b-direction), LIN (1 per gp)
   std::vector<Item> items;
   if (cfg.mesh_field >= 0) {
     for (int gp = 0; gp < 9; ++gp)
@@ -173,7 +173,8 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
           if (cfg.fdof[cfg.mesh_field][j] < 0) continue;
           items.push_back(Item{IT_GEO_A, (uint8_t)gp, (uint8_t)gam, (uint8_t)j});
         }
-    for (int gp = 0; gp < 9; ++gp) items.push_back(Item{IT_GEO_B, (uint8_t)gp, 0, 0});
+    for (int gp = 0; gp < 9; ++gp)
+      for (int k = 0; k < 3; ++k) items.push_back(Item{IT_GEO_B, (uint8_t)gp, (uint8_t)k, 0});
   }
   for (int gp = 0; gp < 9; ++gp) items.push_back(Item{IT_LIN, (uint8_t)gp, 0, 0});
   if ((int)items.size() > MAF_MAX_ITEMS) throw std::runtime_error("item table overflow");
@@ -319,7 +320,7 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
       d.svj = (int16_t)cfg.cnc[F_V][g];
       d.aldv = (int16_t)cfg.ald[F_V];
     }
-    d.c0 = (uint8_t)b.c0; d.d0 = (uint8_t)b.d0; d.kind = (uint8_t)b.kind; d.npcg = (uint8_t)cfg.npc[g];
+    d.c0 = (uint8_t)b.c0; d.d0 = (uint8_t)b.d0; d.kind = (uint8_t)b.kind; d.npcf = (uint8_t)cfg.npc[f];
     d.mesh = (uint8_t)b.mesh; d.qterm = (uint8_t)b.qterm; d.fused = (uint8_t)b.fused; d.tr = (uint8_t)b.tr; d.db = (uint8_t)b.db;
     for (int q = 0; q < 3; ++q) {
       d.ic[q] = q < cfg.npc[f] ? (uint8_t)cfg.pcomp[f][q] : 0;
