@@ -15,7 +15,7 @@
 #include "maf_math.cuh"
 
 #ifndef MAF_SMALL_UNROLL
-#define MAF_SMALL_UNROLL 1
+#define MAF_SMALL_UNROLL 3   // Gauss-point loop of the short blocks (measured +3 % once each kernel carries one tangent phase)
 #endif
 constexpr int kSmallUnroll = MAF_SMALL_UNROLL;
 #ifndef MAF_BIG_UNROLL
@@ -365,10 +365,16 @@ MAF_HD void phase_interp(int tid, int nt, const Config& cfg, const double* fr, d
     else if (q == 33) { ch = CH_N; src = cfg.o_cl; }
     else { ch = CH_N; src = cfg.o_cp; }
     const double* ph = fr + cfg.o_phi + PHI_GP * gp + PHI_C * ch;
-    double s = 0.0;
+    double s3[3];   // one partial sum per node row a2: three short dependency chains instead of one of nine
 #pragma unroll
-    for (int a = 0; a < 9; ++a) s += fr[src + a] * ph[4 * (a / 3) + (a % 3)];
-    sm[cfg.o_E + E_STRIDE * gp + q] = s;
+    for (int a2 = 0; a2 < 3; ++a2) {
+      const dbl2 p01 = ld2(ph + 4 * a2);
+      const double p2 = ph[4 * a2 + 2];
+      s3[a2] = fr[src + 3 * a2] * p01.x;
+      s3[a2] += fr[src + 3 * a2 + 1] * p01.y;
+      s3[a2] += fr[src + 3 * a2 + 2] * p2;
+    }
+    sm[cfg.o_E + E_STRIDE * gp + q] = (s3[0] + s3[1]) + s3[2];
   }
 }
 
@@ -623,7 +629,8 @@ MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const double* fr,
       if (r_stage) r_stage[k] = 0.0;
       continue;
     }
-    double s = 0.0;
+    double s3[3] = {0.0, 0.0, 0.0};   // independent partial sums (the Gauss-point loop is a latency chain otherwise)
+#pragma unroll 3
     for (int gp = 0; gp < 9; ++gp) {
       const double* Sg = sm + cfg.o_S + S_STRIDE * gp;
       const double* ph = fr + cfg.o_phi + PHI_GP * gp + phi_a(a);
@@ -636,8 +643,9 @@ MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const double* fr,
       } else {
         t = Sg[f == F_L ? S_L : S_P] * ph[0];
       }
-      s += fr[cfg.o_w + gp] * t;
+      s3[gp % 3] += fr[cfg.o_w + gp] * t;
     }
+    double s = (s3[0] + s3[1]) + s3[2];
     if (f == F_L || (f == F_P)) {  // Dohrmann-Bochev projection of the nodal lambda / pm (FiniteElement.jl:323-327)
       const double* nod = fr + (f == F_L ? cfg.o_cl : cfg.o_cp);
       double t = 0.0;
