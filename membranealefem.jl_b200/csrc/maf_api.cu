@@ -98,6 +98,8 @@ area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __
     if (blockIdx.x + G < ne) gather_ids_async(tid, T, el_nxt, ids0 + MAF_IDS_INTS);
     async_wait_all();
   }
+  // (staggering the resident CTAs of an SM by a fraction of an element time with __nanosleep: no change -- they are
+  // not in lockstep, the phases simply add up at this occupancy)
   int cur = 0;
 #ifdef MAF_PHASE_TIMING
   long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_last = maf_clock();
@@ -115,21 +117,29 @@ area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __
       el_nxt = el_ids;
       if (kn + 2 * G < ne) el_ids = order[kn + 2 * G];
     }
+#ifndef MAF_STUB_INTERP
     phase_interp(tid, MAF_NT, cfg, fr, sm);
+#endif
     MAF_TICK(1)
     __syncthreads();
     MAF_TICK(2)
+#ifndef MAF_STUB_GAUSS   // MAF_STUB_*: timing-only builds that drop one phase (wrong results; tools/build_variant.sh)
     phase_gauss<MOTION>(tid, cfg, dt, fr, sm);
+#endif
     MAF_TICK(3)
     __syncthreads();
     MAF_TICK(4)
     MAF_TICK(5)
     // (forming the residual on the warp of the IT_LIN items before this barrier was measured: -19 %, that warp
     // becomes the critical path of the Gauss phase)
+#ifndef MAF_STUB_RESIDUAL
     phase_residual(tid, MAF_NT, cfg, fr, sm, r_gl, STAGED ? st.rel + 72 * (el - e0) : nullptr);
+#endif
     if (!STAGED) {
       KSink sink{nzval, nullptr, 0};
+#ifndef MAF_STUB_TANGENT
       phase_tangent(tid, cfg, fr, sm, sink);
+#endif
     } else {
       KSink sink{nullptr, st.kel + (size_t)81 * st.nij * (el - e0), st.nij};
       phase_tangent(tid, cfg, fr, sm, sink);

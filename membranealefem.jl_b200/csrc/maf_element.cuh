@@ -161,7 +161,11 @@ MAF_HD void atomic_add(double* p, double v) {
   asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
 #else
+#if defined(MAF_STUB_RED)   // timing-only build: the reduction is replaced by a store the compiler cannot drop
+MAF_HD void atomic_add(double* p, double v) { if (v == 1.2345e-300) *p = v; }
+#else
 MAF_HD void atomic_add(double* p, double v) { atomicAdd(p, v); }
+#endif
 #endif
 #else
 MAF_HD void atomic_add(double* p, double v) { *p += v; }
@@ -1002,7 +1006,15 @@ MAF_HD void phase_tangent(int tid, const Config& cfg, const double* fr, double* 
     const int id = cfg.chunk_slot[r * nwarps + warp];
     if (id < 0) continue;
     const Chunk ch = cfg.chunks[id];
+#if defined(MAF_PHASE_TIMING) && defined(__CUDA_ARCH__)
+    __syncwarp();
+    const long long t0 = clock64();
+#endif
     if (lane < ch.count) phase_tangent_task(cfg, cfg.td[ch.blk], ch.first + lane, fr, sm, sink);
+#if defined(MAF_PHASE_TIMING) && defined(__CUDA_ARCH__)
+    __syncwarp();
+    if (lane == 0) atomicAdd(&g_chunk_cycles[id], (unsigned long long)(clock64() - t0));
+#endif
   }
 #endif
 }
