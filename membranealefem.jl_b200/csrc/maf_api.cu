@@ -138,11 +138,11 @@ area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __
     if (!STAGED) {
       KSink sink{nzval, nullptr, 0};
 #ifndef MAF_STUB_TANGENT
-      phase_tangent(tid, cfg, fr, sm, sink);
+      phase_tangent<MOTION>(tid, cfg, fr, sm, sink);
 #endif
     } else {
       KSink sink{nullptr, st.kel + (size_t)81 * st.nij * (el - e0), st.nij};
-      phase_tangent(tid, cfg, fr, sm, sink);
+      phase_tangent<MOTION>(tid, cfg, fr, sm, sink);
     }
     async_wait_all();
     MAF_TICK(6)

@@ -39,7 +39,7 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   cfg.motion = motion;
   cfg.ndf = ndf;
   cfg.nthreads = nthreads;
-  cfg.mat = Material{kb, kg, zv, pn, adb, am};
+  cfg.mat = Material{kb, kg, zv, pn, adb, am, adb / zv};
   cfg.dbscale = adb / zv;
   cfg.ncomp[F_V] = 3; cfg.ncomp[F_M] = 3; cfg.ncomp[F_L] = 1; cfg.ncomp[F_P] = 1;
   for (int f = 0; f < NFIELD; ++f)

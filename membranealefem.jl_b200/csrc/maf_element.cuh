@@ -561,7 +561,7 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const 
   Sg[S_L] = S.Sl;
   Sg[S_P] = S.Sp;
   // ---- closed-form columns (all factors below are metric quantities of this Gauss point) ----
-  const double wJ = w * g.J, zv = cfg.mat.zv, am = cfg.mat.am, kdb = cfg.mat.adb / cfg.mat.zv;
+  const double wJ = w * g.J, zv = cfg.mat.zv, am = cfg.mat.am, kdb = cfg.mat.kdb;
   const double Aup[2][2] = {{g.A11, g.A12}, {g.A12, g.A22}};
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
@@ -666,7 +666,7 @@ MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const double* fr,
 //   first contraction  u[d]  = sum_c Phi^c_a A[(i,c)][(j,d)]
 //   second contraction K[b] += sum_d u[d] Phi^d_b
 // ---------------------------------------------------------------------------------------------------------
-template <int NR, int NC>
+template <int NR, int NC, int UNR>
 MAF_HD void block_accumulate(const double* __restrict__ A0, int asize, int ald, const double* __restrict__ Phi,
                              int c0, int d0, int a, double acc[9]) {
 #pragma unroll
@@ -674,7 +674,7 @@ MAF_HD void block_accumulate(const double* __restrict__ A0, int asize, int ald, 
   const int pa = phi_a(a);
   // the blocks of the first-derivative channels are short: three Gauss points per trip so that the loads of one
   // overlap the arithmetic of the others (a trip of one point is all shared-memory latency)
-#pragma unroll kSmallUnroll
+#pragma unroll UNR
   for (int gp = 0; gp < 9; ++gp) {
     const double* Ag = A0 + (size_t)asize * gp;
     const double* Pg = Phi + PHI_GP * gp;
@@ -928,8 +928,13 @@ MAF_HD void scatter_col(const Config& cfg, const double* fr, const KSink& sink, 
 #endif
 }
 
+// Gauss-point loop of the short blocks: three points per trip for ALE / LAG (measured +3 %); EUL loses 5 % with it
+template <int MOTION> struct SmallUnroll { static constexpr int value = MOTION == M_EUL ? 1 : kSmallUnroll; };
+
+template <int MOTION>
 MAF_HD void phase_tangent_task(const Config& cfg, const TaskDesc& d, int t, const double* fr, const double* sm,
                                const KSink& sink) {
+  constexpr int U = SmallUnroll<MOTION>::value;
   // row component fastest: the lanes of a chunk share the column (b, J) and differ in the row (a, I), whose slots are
   // adjacent in the CSC column (node-major numbering) -- their reductions fall into the same 32-byte sectors
   const int a = t % 9, ij = t / 9;
@@ -959,9 +964,9 @@ MAF_HD void phase_tangent_task(const Config& cfg, const TaskDesc& d, int t, cons
     return;
   }
   switch (d.kind) {
-    case 0: block_accumulate<1, 1>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc); break;
-    case 3: block_accumulate<2, 1>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc); break;
-    case 4: block_accumulate<2, 2>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc); break;
+    case 0: block_accumulate<1, 1, U>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc); break;
+    case 3: block_accumulate<2, 1, U>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc); break;
+    case 4: block_accumulate<2, 2, U>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc); break;
     case 5: block_accumulate_mesh<3>(A0, cfg.asize, ald, boff, Phi, FG, G, d.c0, a, i, j, d.qterm, acc); break;
     case 6: block_accumulate_mesh<5>(A0, cfg.asize, ald, boff, Phi, FG, G, d.c0, a, i, j, d.qterm, acc); break;
     default: block_accumulate_mesh<6>(A0, cfg.asize, ald, boff, Phi, FG, G, d.c0, a, i, j, d.qterm, acc); break;
@@ -977,6 +982,7 @@ MAF_HD void phase_tangent_task(const Config& cfg, const TaskDesc& d, int t, cons
 #if defined(MAF_PHASE_TIMING) && defined(__CUDACC__)
 __device__ unsigned long long g_chunk_cycles[MAF_MAX_CHUNKS];   // profiling build: cycles per tangent chunk
 #endif
+template <int MOTION>
 MAF_HD void phase_tangent(int tid, const Config& cfg, const double* fr, double* sm, const KSink& sink) {
   const int warp = tid >> 5, lane = tid & 31;
 #if defined(__CUDA_ARCH__) && defined(MAF_DYNAMIC_SCHED)   // variant, measured 4 % slower than the static plan
@@ -993,7 +999,7 @@ MAF_HD void phase_tangent(int tid, const Config& cfg, const double* fr, double* 
 #if defined(MAF_PHASE_TIMING)
     const long long t0 = clock64();
 #endif
-    if (lane < ch.count) phase_tangent_task(cfg, cfg.td[ch.blk], ch.first + lane, fr, sm, sink);
+    if (lane < ch.count) phase_tangent_task<MOTION>(cfg, cfg.td[ch.blk], ch.first + lane, fr, sm, sink);
 #if defined(MAF_PHASE_TIMING)
     __syncwarp();
     if (lane == 0) atomicAdd(&g_chunk_cycles[id], (unsigned long long)(clock64() - t0));
@@ -1010,7 +1016,7 @@ MAF_HD void phase_tangent(int tid, const Config& cfg, const double* fr, double* 
     __syncwarp();
     const long long t0 = clock64();
 #endif
-    if (lane < ch.count) phase_tangent_task(cfg, cfg.td[ch.blk], ch.first + lane, fr, sm, sink);
+    if (lane < ch.count) phase_tangent_task<MOTION>(cfg, cfg.td[ch.blk], ch.first + lane, fr, sm, sink);
 #if defined(MAF_PHASE_TIMING) && defined(__CUDA_ARCH__)
     __syncwarp();
     if (lane == 0) atomicAdd(&g_chunk_cycles[id], (unsigned long long)(clock64() - t0));

@@ -65,6 +65,7 @@ enum { CH_N = 0, CH_N1 = 1, CH_N2 = 2, CH_N11 = 3, CH_N22 = 4, CH_N12 = 5, NCH =
 
 struct Material {
   double kb, kg, zv, pn, adb, am;
+  double kdb;   // adb / zv, formed once on the host (an FP64 division per Gauss-point evaluation otherwise)
 };
 
 // Generalised stresses at one Gauss point. Sv/Sm: [channel][component]; Sl, Sp scalars (channel N only).
@@ -77,6 +78,21 @@ template <class T> struct GpStress {
   T Sm[NCH][3];
   T Sl, Sp;
 };
+
+// 1/x, sqrt(x), 1/sqrt(x) of the metric determinant with ONE division and one square root (FP64 division and square
+// root are long instruction sequences): 1/sqrt(x) = sqrt(x) * (1/x); the derivative parts need no further division.
+MAF_HD void inv_sqrt_inv(double x, double& ix, double& s, double& is) {
+  ix = 1.0 / x;
+  s = sqrt(x);
+  is = s * ix;
+}
+MAF_HD void inv_sqrt_inv(Dual x, Dual& ix, Dual& s, Dual& is) {
+  const double r = 1.0 / x.v, sq = sqrt(x.v), isq = sq * r;
+  ix = Dual(r, -(r * r) * x.d);
+  const double hd = 0.5 * x.d;
+  s = Dual(sq, hd * isq);
+  is = Dual(isq, -(hd * isq) * r);
+}
 
 // Metric quantities that depend on the tangent vectors only (GeoDynStress.jl:117-123).
 template <class TA> struct GpGeom {
@@ -91,12 +107,10 @@ template <class TA> MAF_HD void gp_geom(const TA a[2][3], GpGeom<TA>& g) {
   TA a12 = a[0][0] * a[1][0] + a[0][1] * a[1][1] + a[0][2] * a[1][2];
   TA a22 = a[1][0] * a[1][0] + a[1][1] * a[1][1] + a[1][2] * a[1][2];
   TA det = a11 * a22 - a12 * a12;
-  g.idet = 1.0 / det;
+  inv_sqrt_inv(det, g.idet, g.J, g.iJ);
   g.A11 = a22 * g.idet;
   g.A22 = a11 * g.idet;
   g.A12 = -(a12 * g.idet);
-  g.J = dsqrt(det);
-  g.iJ = 1.0 / g.J;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     g.up[0][i] = a[0][i] * g.A11 + a[1][i] * g.A12;
@@ -173,7 +187,7 @@ MAF_HD void gp_core(const GpGeom<TA>& g, const TA a[2][3], const TB b[3], const 
     out.Sv[CH_N][i] = (-mat.pn) * (J * g.n[i]);
   }
   // ---- lambda row (:298-299) ----
-  out.Sl = J * (g00 + g11) - (mat.adb / mat.zv) * lam;
+  out.Sl = J * (g00 + g11) - mat.kdb * lam;
 
   // ---- mesh rows ----
 #pragma unroll
@@ -212,7 +226,7 @@ MAF_HD void gp_core(const GpGeom<TA>& g, const TA a[2][3], const TB b[3], const 
       out.Sm[CH_N][i] = -(J * g.n[i]) * pm;
       nd = nd + g.n[i] * (vm[i] - v[i]);
     }
-    out.Sp = -(J * nd) - (mat.adb / mat.zv) * pm;
+    out.Sp = -(J * nd) - mat.kdb * pm;
   }
 }
 

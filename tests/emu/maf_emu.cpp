@@ -51,7 +51,7 @@ static void run_area(const HostModel& M, const Tables& T, const double* xms, con
     KSink sink{nzval, nullptr, 0};
     if (kel) sink = KSink{nullptr, kel + (size_t)81 * GH->nij * (el - e0), GH->nij};
     for (int t = 0; t < nt; ++t) phase_residual(t, nt, cfg, fr, sm, r, rel ? rel + 72 * (el - e0) : nullptr);
-    for (int t = 0; t < nt; ++t) phase_tangent(t, cfg, fr, sm, sink);
+    for (int t = 0; t < nt; ++t) phase_tangent<MOTION>(t, cfg, fr, sm, sink);
   }
 }
 
