@@ -136,6 +136,12 @@ int maf_launch_count(maf_handle* h, int64_t* n);
  * out[2] dynamic shared memory bytes per CTA, out[3] resident CTAs per SM, out[4] SM count. */
 int maf_kernel_info(maf_handle* h, int64_t* out5);
 
+/* The static plan of the area kernel's contraction phase as text: "c,c,c/c,c/..." = the chunk ids (<= 32 tangent
+ * tasks of one block each) that every warp of the CTA executes, in order. The environment variable MAF_PLAN (same
+ * format) replaces the built-in plan at maf_create (tools/tune_plan.py searches plans on the GPU). No reference
+ * counterpart: the reference's element loop (FiniteElement.jl:98-140) is scheduled by Julia's task runtime. */
+int maf_chunk_plan(maf_handle* h, char* text, int64_t cap);
+
 /* Multi-GPU (one process per GPU, every process holds the same mesh tables): restrict this handle to the elements
  * [el_first, el_last] (1-based, inclusive) -- contiguous element ids are strips of element rows (Mesh.jl:582-588).
  * Because unknowns are numbered node-major (Mesh.jl:276-284) a strip touches one contiguous range of rows of r and

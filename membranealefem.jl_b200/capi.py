@@ -43,7 +43,7 @@ _lib = None
 
 EXPORTS = ["maf_create", "maf_destroy", "maf_last_error", "maf_nnz", "maf_pattern", "maf_assemble",
            "maf_assemble_device", "maf_device_buffers", "maf_stream", "maf_sync", "maf_timings", "maf_launch_count",
-           "maf_kernel_info", "maf_set_element_range", "maf_range_info", "maf_fp64_peak",
+           "maf_kernel_info", "maf_chunk_plan", "maf_set_element_range", "maf_range_info", "maf_fp64_peak",
            "maf_debug_phase_cycles", "maf_state_set", "maf_state_get", "maf_state_update", "maf_state_predict",
            "maf_assemble_resident", "maf_elem_v_residuals"]
 
@@ -74,6 +74,7 @@ def load_library(path=None):
     L.maf_timings.argtypes = [C.c_void_p, _F64P]
     L.maf_launch_count.argtypes = [C.c_void_p, _I64P]
     L.maf_kernel_info.argtypes = [C.c_void_p, _I64P]
+    L.maf_chunk_plan.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     L.maf_set_element_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     L.maf_range_info.argtypes = [C.c_void_p, _I64P]
     L.maf_fp64_peak.argtypes = [C.c_int, _F64P]
@@ -256,6 +257,12 @@ class Assembler:
         o = np.zeros(5, dtype=np.int64)
         self._check(self.L.maf_kernel_info(self.h, _ptr(o, C.c_int64)))
         return dict(zip(["threads_per_cta", "elements_per_cta", "smem_bytes", "ctas_per_sm", "sm_count"], o.tolist()))
+
+    def chunk_plan(self):
+        """Plan of the contraction phase, "c,c/c,c/..." = chunk ids per warp in execution order."""
+        buf = C.create_string_buffer(1024)
+        self._check(self.L.maf_chunk_plan(self.h, buf, 1024))
+        return buf.value.decode()
 
     def set_element_range(self, el_first, el_last):
         self._check(self.L.maf_set_element_range(self.h, el_first, el_last))

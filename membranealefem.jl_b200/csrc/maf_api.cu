@@ -972,6 +972,28 @@ int maf_kernel_info(maf_handle* h, int64_t* out5) {
   MAF_API_END(h)
 }
 
+int maf_chunk_plan(maf_handle* h, char* text, int64_t cap) {
+  MAF_API_BEGIN(h)
+  if (!text || cap < 1) throw std::runtime_error("null output pointer");
+  const Config& c = h->M.cfg;
+  const int nw = c.nthreads / 32;
+  std::string s;
+  for (int w = 0; w < nw; ++w) {
+    if (w) s += '/';
+    bool first = true;
+    for (int r = 0; r < c.task_rounds; ++r) {
+      const int id = c.chunk_slot[r * nw + w];
+      if (id < 0) continue;
+      if (!first) s += ',';
+      s += std::to_string(id);
+      first = false;
+    }
+  }
+  if ((int64_t)s.size() + 1 > cap) throw std::runtime_error("plan text buffer too small");
+  std::memcpy(text, s.c_str(), s.size() + 1);
+  MAF_API_END(h)
+}
+
 int maf_set_element_range(maf_handle* h, int64_t el_first, int64_t el_last) {
   MAF_API_BEGIN(h)
   if (el_first < 1 || el_last > h->M.numel || el_first > el_last + 1)

@@ -3,6 +3,7 @@
 // Pure C++ (no CUDA) so that the CPU emulation harness in tests/ builds the very same tables.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -30,6 +31,18 @@ inline int kind_cost(int kind, bool fused, bool tr) {
   if (tr) return MAF_TASK_FIXED + tab[kind][0] * tab[kind][1] + 9 * tab[kind][0];
   if (tab[kind][1] == 5) return MAF_TASK_FIXED + 5 * tab[kind][0] + 8 + 42;   // sum-factorised mesh-column blocks
   return MAF_TASK_FIXED + tab[kind][0] * tab[kind][1] + 9 * tab[kind][1];
+}
+
+// chunk plans found by tools/tune_plan.py on B200 (1001 x 1001 patch), keyed by motion and chunk count; NULL: heuristic
+inline const char* tuned_plan(int motion, int nchunks, int nwarps) {
+  if (nwarps != 4) return nullptr;
+#ifdef MAF_NO_TUNED_PLAN
+  return nullptr;
+#endif
+  if (motion == M_ALEVB && nchunks == 14) return "1,12,11/2,10/13,4,6,3,9/0,5,7,8";             // +1.4 % over the heuristic
+  if (motion == M_EUL && nchunks == 16) return "6,10,9/8,7,13,15/3,4,2,12/14,5,0,1,11";         // +3.3 %
+  if (motion == M_LAG && nchunks == 6) return "1/2/0,4/3,5";                                     // +0.6 %
+  return nullptr;
 }
 
 // dofs8: column (1-based) of vx vy vz vmx vmy vmz lambda pm, or 0 (Mesh.dofs, Bc.jl:414-431)
@@ -251,6 +264,34 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
         if (load[w] < load[wbest]) wbest = w;
       plan[wbest].push_back(k);
       load[wbest] += chs[k].cost;
+    }
+    // A tuned plan replaces the heuristic one: which chunks run side by side on the SM (shared-memory pipe against
+    // FP64 pipe) matters more than the balance of the warps, and no cost model captured that (tools/tune_plan.py
+    // searches the plans on the GPU). "c,c,c/c,c/..." = chunk ids per warp in execution order; MAF_PLAN overrides.
+    {
+      const char* text = std::getenv("MAF_PLAN");
+      if (!text || !*text) text = tuned_plan(motion, cfg.nchunks, nwarps);
+      if (text && *text) {
+        std::vector<std::vector<int>> tp(1);
+        std::vector<int> seen(cfg.nchunks, 0);
+        bool ok = true;
+        int v = -1;
+        for (const char* c = text;; ++c) {
+          if (*c >= '0' && *c <= '9') { v = (v < 0 ? 0 : v * 10) + (*c - '0'); continue; }
+          if (v >= 0) {
+            if (v >= cfg.nchunks || seen[v]++) ok = false;
+            else tp.back().push_back(v);
+            v = -1;
+          }
+          if (*c == '/') tp.emplace_back();
+          else if (*c != ',' && *c != 0) ok = false;
+          if (*c == 0) break;
+        }
+        for (int k = 0; k < cfg.nchunks; ++k) ok = ok && seen[k] == 1;
+        if (!ok || (int)tp.size() > nwarps) throw std::runtime_error(std::string("invalid chunk plan: ") + text);
+        tp.resize(nwarps);
+        plan = tp;
+      }
     }
     cfg.task_rounds = 0;
     for (int w = 0; w < nwarps; ++w) cfg.task_rounds = std::max(cfg.task_rounds, (int)plan[w].size());

@@ -22,6 +22,10 @@ constexpr int kSmallUnroll = MAF_SMALL_UNROLL;
 #define MAF_BIG_UNROLL 3
 #endif
 constexpr int kBigUnroll = MAF_BIG_UNROLL;   // Gauss-point loop of the mesh-column blocks (measured: LAG +4 %)
+#ifndef MAF_FUSED_UNROLL
+#define MAF_FUSED_UNROLL 1   // inner (g1) loop of the fused ALEVB block
+#endif
+constexpr int kFusedUnroll = MAF_FUSED_UNROLL;
 #ifndef MAF_SCATTER_PRELOAD
 #define MAF_SCATTER_PRELOAD 0
 #endif
@@ -666,84 +670,119 @@ MAF_HD void phase_residual(int tid, int nt, const Config& cfg, const double* fr,
 //   first contraction  u[d]  = sum_c Phi^c_a A[(i,c)][(j,d)]
 //   second contraction K[b] += sum_d u[d] Phi^d_b
 // ---------------------------------------------------------------------------------------------------------
+// Sum factorisation over the Gauss points. The basis is a tensor product, Phi^d_b(gp) = f^{o1(d)}_{b1}(g1) g^{o2(d)}_{b2}(g2)
+// with gp = g1 + 3 g2 (GpBasisFn.jl:102-110, :350), so the second contraction
+//   K[b1 + 3 b2] += sum_{g2} g^{o2}_{b2}(g2) * ( sum_{g1} f^{o1}_{b1}(g1) u_d(g1, g2) )
+// accumulates three partial sums T[b1] per channel over the inner direction and expands them to the nine entries
+// once per g2 instead of once per Gauss point: 3 + 9/3 = 6 instead of 9 multiply-adds and 3 + 3/3 = 4 instead of 9
+// shared-memory words per channel and Gauss point (the shared-memory pipe is the busiest unit of the kernel).
+// Derivative orders of the channels N N1 N2 N11 N22 N12 in the two directions; FG[gp][18] holds f[order][b1] at
+// 3 order + b1 and g[order][b2] at 9 + 3 order + b2 (build_basis_block).
+MAF_HD int ch_fo(int c) { return 3 * ((c == CH_N1 || c == CH_N12) ? 1 : (c == CH_N11 ? 2 : 0)); }
+MAF_HD int ch_go(int c) { return 9 + 3 * ((c == CH_N2 || c == CH_N12) ? 1 : (c == CH_N22 ? 2 : 0)); }
+
 template <int NR, int NC, int UNR>
 MAF_HD void block_accumulate(const double* __restrict__ A0, int asize, int ald, const double* __restrict__ Phi,
-                             int c0, int d0, int a, double acc[9]) {
+                             const double* __restrict__ FG, int c0, int d0, int a, double acc[9]) {
 #pragma unroll
   for (int b = 0; b < 9; ++b) acc[b] = 0.0;
   const int pa = phi_a(a);
-  // the blocks of the first-derivative channels are short: three Gauss points per trip so that the loads of one
-  // overlap the arithmetic of the others (a trip of one point is all shared-memory latency)
+  int fo[NC], go[NC];
+#pragma unroll
+  for (int d = 0; d < NC; ++d) { fo[d] = ch_fo(d0 + d); go[d] = ch_go(d0 + d); }
+#pragma unroll 1
+  for (int g2 = 0; g2 < 3; ++g2) {
+    double T[NC][3];
+#pragma unroll
+    for (int d = 0; d < NC; ++d) { T[d][0] = 0.0; T[d][1] = 0.0; T[d][2] = 0.0; }
+    // the blocks of the first-derivative channels are short: the three points of a row per trip so that the loads
+    // of one overlap the arithmetic of the others (a trip of one point is all shared-memory latency)
 #pragma unroll UNR
-  for (int gp = 0; gp < 9; ++gp) {
-    const double* Ag = A0 + (size_t)asize * gp;
-    const double* Pg = Phi + PHI_GP * gp;
-    double u[NC];
+    for (int g1 = 0; g1 < 3; ++g1) {
+      const int gp = g1 + 3 * g2;
+      const double* Ag = A0 + (size_t)asize * gp;
+      const double* Pg = Phi + PHI_GP * gp;
+      const double* Fg = FG + FG_STRIDE * gp;
+      double u[NC];
 #pragma unroll
-    for (int d = 0; d < NC; ++d) u[d] = 0.0;
+      for (int d = 0; d < NC; ++d) u[d] = 0.0;
 #pragma unroll
-    for (int c = 0; c < NR; ++c) {
-      const double p = Pg[PHI_C * (c0 + c) + pa];
+      for (int c = 0; c < NR; ++c) {
+        const double p = Pg[PHI_C * (c0 + c) + pa];
 #pragma unroll
-      for (int d = 0; d < NC; ++d) u[d] += p * Ag[c * ald + d];
+        for (int d = 0; d < NC; ++d) u[d] += p * Ag[c * ald + d];
+      }
+#pragma unroll
+      for (int d = 0; d < NC; ++d)
+#pragma unroll
+        for (int b1 = 0; b1 < 3; ++b1) T[d][b1] += u[d] * Fg[fo[d] + b1];
     }
+    const double* Gg = FG + FG_STRIDE * (3 * g2);
 #pragma unroll
     for (int d = 0; d < NC; ++d)
 #pragma unroll
       for (int b2 = 0; b2 < 3; ++b2) {
-        const dbl2 q01 = ld2(Pg + PHI_C * (d0 + d) + 4 * b2);
-        const double q2 = Pg[PHI_C * (d0 + d) + 4 * b2 + 2];
-        acc[3 * b2] += u[d] * q01.x;
-        acc[3 * b2 + 1] += u[d] * q01.y;
-        acc[3 * b2 + 2] += u[d] * q2;
+        const double gv = Gg[go[d] + b2];
+#pragma unroll
+        for (int b1 = 0; b1 < 3; ++b1) acc[b1 + 3 * b2] += T[d][b1] * gv;
       }
   }
 }
 
 // transposed form for blocks with fewer row than column channels: v[c] = sum_d A[(i,c)][(j,d)] Phi^d_b, then
-// K[a] += sum_c Phi^c_a v[c] for the 9 row nodes a
+// K[a] += sum_c Phi^c_a v[c] for the 9 row nodes a (sum-factorised like the direct form)
 template <int NR, int NC>
 MAF_HD void block_accumulate_tr(const double* __restrict__ A0, int asize, int ald, const double* __restrict__ Phi,
-                                int c0, int d0, int b, double acc[9]) {
+                                const double* __restrict__ FG, int c0, int d0, int b, double acc[9]) {
 #pragma unroll
   for (int a = 0; a < 9; ++a) acc[a] = 0.0;
   const int pb = phi_a(b);
+  int fo[NR], go[NR];
+#pragma unroll
+  for (int c = 0; c < NR; ++c) { fo[c] = ch_fo(c0 + c); go[c] = ch_go(c0 + c); }
 #pragma unroll 1
-  for (int gp = 0; gp < 9; ++gp) {
-    const double* Ag = A0 + (size_t)asize * gp;
-    const double* Pg = Phi + PHI_GP * gp;
-    double v[NR];
+  for (int g2 = 0; g2 < 3; ++g2) {
+    double T[NR][3];
 #pragma unroll
-    for (int c = 0; c < NR; ++c) v[c] = 0.0;
+    for (int c = 0; c < NR; ++c) { T[c][0] = 0.0; T[c][1] = 0.0; T[c][2] = 0.0; }
+#pragma unroll 1
+    for (int g1 = 0; g1 < 3; ++g1) {
+      const int gp = g1 + 3 * g2;
+      const double* Ag = A0 + (size_t)asize * gp;
+      const double* Pg = Phi + PHI_GP * gp;
+      const double* Fg = FG + FG_STRIDE * gp;
+      double v[NR];
 #pragma unroll
-    for (int d = 0; d < NC; ++d) {
-      const double q = Pg[PHI_C * (d0 + d) + pb];
+      for (int c = 0; c < NR; ++c) v[c] = 0.0;
 #pragma unroll
-      for (int c = 0; c < NR; ++c) v[c] += q * Ag[c * ald + d];
+      for (int d = 0; d < NC; ++d) {
+        const double q = Pg[PHI_C * (d0 + d) + pb];
+#pragma unroll
+        for (int c = 0; c < NR; ++c) v[c] += q * Ag[c * ald + d];
+      }
+#pragma unroll
+      for (int c = 0; c < NR; ++c)
+#pragma unroll
+        for (int a1 = 0; a1 < 3; ++a1) T[c][a1] += v[c] * Fg[fo[c] + a1];
     }
+    const double* Gg = FG + FG_STRIDE * (3 * g2);
 #pragma unroll
     for (int c = 0; c < NR; ++c)
 #pragma unroll
       for (int a2 = 0; a2 < 3; ++a2) {
-        const dbl2 p01 = ld2(Pg + PHI_C * (c0 + c) + 4 * a2);
-        const double p2 = Pg[PHI_C * (c0 + c) + 4 * a2 + 2];
-        acc[3 * a2] += v[c] * p01.x;
-        acc[3 * a2 + 1] += v[c] * p01.y;
-        acc[3 * a2 + 2] += v[c] * p2;
+        const double gv = Gg[go[c] + a2];
+#pragma unroll
+        for (int a1 = 0; a1 < 3; ++a1) acc[a1 + 3 * a2] += T[c][a1] * gv;
       }
   }
 }
 
-// the 1-D factors of one Gauss point: f[order][b1] at fg[3*order + b1], g[order][b2] at fg[9 + 3*order + b2]
-MAF_HD void load_fg(const double* Fg, double fg[18]) {
-#pragma unroll
-  for (int q = 0; q < 9; ++q) { const dbl2 v2 = ld2(Fg + 2 * q); fg[2 * q] = v2.x; fg[2 * q + 1] = v2.y; }
-}
-
 // Mesh-column block: trial channels N1,N2 (per mesh dof j, stored) and N11,N22,N12 (expanded on the fly from the
 // b-direction columns):  A[(i,c)][(j,N_k)] = n_j * Ab_k[(i,c)] - [c = N_mu] a^mu_j * (w dt Q_k[i]).
-// The second contraction is sum-factorised over the tensor-product structure of the basis
-// (Phi^d_b = f^{d1}_{b1} g^{d2}_{b2}):  sum_d u_d Phi^d_b = f1 (u_N1 g0 + u_N12 g1) + f0 (u_N2 g1 + u_N22 g2) + f2 u_N11 g0.
+// Second contraction, sum-factorised over the tensor-product structure of the basis (f = direction 1, g = direction 2,
+// superscript = derivative order):
+//   sum_d u_d Phi^d_b = g0_{b2} (f1_{b1} u_N1 + f2_{b1} u_N11) + g1_{b2} (f1_{b1} u_N12 + f0_{b1} u_N2) + g2_{b2} f0_{b1} u_N22
+// with the three brackets accumulated over the inner Gauss direction g1 and expanded once per g2.
 template <int NR>
 MAF_HD void block_accumulate_mesh(const double* __restrict__ A0, int asize, int ald, int boff,
                                   const double* __restrict__ Phi, const double* __restrict__ FG,
@@ -752,40 +791,49 @@ MAF_HD void block_accumulate_mesh(const double* __restrict__ A0, int asize, int 
 #pragma unroll
   for (int b = 0; b < 9; ++b) acc[b] = 0.0;
   const int pa = phi_a(a);
+#pragma unroll 1
+  for (int g2 = 0; g2 < 3; ++g2) {
+    double X0[3] = {0.0, 0.0, 0.0}, X1[3] = {0.0, 0.0, 0.0}, X2[3] = {0.0, 0.0, 0.0};
 #pragma unroll kBigUnroll
-  for (int gp = 0; gp < 9; ++gp) {
-    const double* Ag = A0 + (size_t)asize * gp;
-    const double* Pg = Phi + PHI_GP * gp + pa;
-    const double* Gg = G + G_STRIDE * gp;
-    double u[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int g1 = 0; g1 < 3; ++g1) {
+      const int gp = g1 + 3 * g2;
+      const double* Ag = A0 + (size_t)asize * gp;
+      const double* Pg = Phi + PHI_GP * gp + pa;
+      const double* Gg = G + G_STRIDE * gp;
+      const double* Fg = FG + FG_STRIDE * gp;
+      double u[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int c = 0; c < NR; ++c) {
-      const double p = Pg[PHI_C * (c0 + c)];
-      const double* row = Ag + c * ald;
-      const dbl2 a01 = ld2(row);          // (j, N1), (j, N2)
-      const dbl2 b01 = ld2(row + boff);   // b-directions 11, 22
-      const double b2v = row[boff + 2];   // b-direction 12
-      u[0] += p * a01.x; u[1] += p * a01.y; u[2] += p * b01.x; u[3] += p * b01.y; u[4] += p * b2v;
+      for (int c = 0; c < NR; ++c) {
+        const double p = Pg[PHI_C * (c0 + c)];
+        const double* row = Ag + c * ald;
+        const dbl2 a01 = ld2(row);          // (j, N1), (j, N2)
+        const dbl2 b01 = ld2(row + boff);   // b-directions 11, 22
+        const double b2v = row[boff + 2];   // b-direction 12
+        u[0] += p * a01.x; u[1] += p * a01.y; u[2] += p * b01.x; u[3] += p * b01.y; u[4] += p * b2v;
+      }
+      const double nj = Gg[G_N + j];
+      double t = 0.0;
+      if (qterm) t = Gg[G_UP + j] * Pg[PHI_C * CH_N1] + Gg[G_UP + 3 + j] * Pg[PHI_C * CH_N2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) u[2 + k] = nj * u[2 + k] - (qterm ? Gg[G_QW + 3 * k + i] : 0.0) * t;
+#pragma unroll
+      for (int b1 = 0; b1 < 3; ++b1) {
+        const double f0 = Fg[b1], f1 = Fg[3 + b1], f2 = Fg[6 + b1];
+        X0[b1] += f1 * u[0]; X0[b1] += f2 * u[2];
+        X1[b1] += f1 * u[4]; X1[b1] += f0 * u[1];
+        X2[b1] += f0 * u[3];
+      }
     }
-    const double nj = Gg[G_N + j];
-    double t = 0.0;
-    if (qterm) t = Gg[G_UP + j] * Pg[PHI_C * CH_N1] + Gg[G_UP + 3 + j] * Pg[PHI_C * CH_N2];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) u[2 + k] = nj * u[2 + k] - (qterm ? Gg[G_QW + 3 * k + i] : 0.0) * t;
-    double fg[18];
-    load_fg(FG + FG_STRIDE * gp, fg);
+    const double* Gq = FG + FG_STRIDE * (3 * g2) + 9;
 #pragma unroll
     for (int b2 = 0; b2 < 3; ++b2) {
-      const double g0 = fg[9 + b2], g1 = fg[12 + b2], g2 = fg[15 + b2];
-      const double t1 = u[0] * g0 + u[4] * g1;   // multiplies f1[b1]   (N1, N12)
-      const double t0 = u[1] * g1 + u[3] * g2;   // multiplies f0[b1]   (N2, N22)
-      const double t2 = u[2] * g0;               // multiplies f2[b1]   (N11)
+      const double g0 = Gq[b2], g1v = Gq[3 + b2], g2v = Gq[6 + b2];
 #pragma unroll
-      for (int b1 = 0; b1 < 3; ++b1) {           // three separate multiply-adds (each contracts to one DFMA)
+      for (int b1 = 0; b1 < 3; ++b1) {
         double sacc = acc[b1 + 3 * b2];
-        sacc += fg[3 + b1] * t1;
-        sacc += fg[b1] * t0;
-        sacc += fg[6 + b1] * t2;
+        sacc += g0 * X0[b1];
+        sacc += g1v * X1[b1];
+        sacc += g2v * X2[b1];
         acc[b1 + 3 * b2] = sacc;
       }
     }
@@ -806,50 +854,61 @@ MAF_HD void block_accumulate_fused(const double* __restrict__ Am, int ald_m, int
   for (int b = 0; b < 9; ++b) { acc_mm[b] = 0.0; acc_vm[b] = 0.0; }
   const int pa = phi_a(a);
 #pragma unroll 1
-  for (int gp = 0; gp < 9; ++gp) {
-    const double* Pg = Phi + PHI_GP * gp + pa;
-    const double* Gg = G + G_STRIDE * gp;
-    const double* Amg = Am + (size_t)asize * gp;
-    const double* Avg = Av + (size_t)asize * gp;
-    double u[5];
-    const double pN = Pg[PHI_C * CH_N];
-    const dbl2 n01 = ld2(Amg);
-    u[0] = pN * n01.x; u[1] = pN * n01.y; u[2] = 0.0; u[3] = 0.0; u[4] = 0.0;
-    const double p1 = Pg[PHI_C * CH_N1], p2 = Pg[PHI_C * CH_N2];
-    const dbl2 c1 = ld2(Avg), c2 = ld2(Avg + ald_v);
-    double dl0 = -u[0], dl1 = -u[1];
-    dl0 += p1 * c1.x; dl1 += p1 * c1.y;
-    dl0 += p2 * c2.x; dl1 += p2 * c2.y;
+  for (int g2 = 0; g2 < 3; ++g2) {
+    double X0[3] = {0.0, 0.0, 0.0}, X1[3] = {0.0, 0.0, 0.0}, X2[3] = {0.0, 0.0, 0.0};
+    double Y0[3] = {0.0, 0.0, 0.0}, Y1[3] = {0.0, 0.0, 0.0};
+#pragma unroll kFusedUnroll
+    for (int g1 = 0; g1 < 3; ++g1) {
+      const int gp = g1 + 3 * g2;
+      const double* Pg = Phi + PHI_GP * gp + pa;
+      const double* Gg = G + G_STRIDE * gp;
+      const double* Amg = Am + (size_t)asize * gp;
+      const double* Avg = Av + (size_t)asize * gp;
+      const double* Fg = FG + FG_STRIDE * gp;
+      double u[5];
+      const double pN = Pg[PHI_C * CH_N];
+      const dbl2 n01 = ld2(Amg);
+      u[0] = pN * n01.x; u[1] = pN * n01.y; u[2] = 0.0; u[3] = 0.0; u[4] = 0.0;
+      const double p1 = Pg[PHI_C * CH_N1], p2 = Pg[PHI_C * CH_N2];
+      const dbl2 c1 = ld2(Avg), c2 = ld2(Avg + ald_v);
+      double dl0 = -u[0], dl1 = -u[1];
+      dl0 += p1 * c1.x; dl1 += p1 * c1.y;
+      dl0 += p2 * c2.x; dl1 += p2 * c2.y;
 #pragma unroll
-    for (int c = 1; c < 6; ++c) {
-      const double p = Pg[PHI_C * c];
-      const double* row = Amg + c * ald_m;
-      const dbl2 a01 = ld2(row);
-      const dbl2 b01 = ld2(row + boff);
-      const double b2v = row[boff + 2];
-      u[0] += p * a01.x; u[1] += p * a01.y; u[2] += p * b01.x; u[3] += p * b01.y; u[4] += p * b2v;
+      for (int c = 1; c < 6; ++c) {
+        const double p = Pg[PHI_C * c];
+        const double* row = Amg + c * ald_m;
+        const dbl2 a01 = ld2(row);
+        const dbl2 b01 = ld2(row + boff);
+        const double b2v = row[boff + 2];
+        u[0] += p * a01.x; u[1] += p * a01.y; u[2] += p * b01.x; u[3] += p * b01.y; u[4] += p * b2v;
+      }
+      const double nj = Gg[G_N + j];
+      const double t = Gg[G_UP + j] * p1 + Gg[G_UP + 3 + j] * p2;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) u[2 + k] = nj * u[2 + k] - Gg[G_QW + 3 * k + i] * t;
+#pragma unroll
+      for (int b1 = 0; b1 < 3; ++b1) {
+        const double f0 = Fg[b1], f1 = Fg[3 + b1], f2 = Fg[6 + b1];
+        X0[b1] += f1 * u[0]; X0[b1] += f2 * u[2];
+        X1[b1] += f1 * u[4]; X1[b1] += f0 * u[1];
+        X2[b1] += f0 * u[3];
+        Y0[b1] += f1 * dl0;
+        Y1[b1] += f0 * dl1;
+      }
     }
-    const double nj = Gg[G_N + j];
-    const double t = Gg[G_UP + j] * p1 + Gg[G_UP + 3 + j] * p2;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) u[2 + k] = nj * u[2 + k] - Gg[G_QW + 3 * k + i] * t;
-    double fg[18];
-    load_fg(FG + FG_STRIDE * gp, fg);
+    const double* Gq = FG + FG_STRIDE * (3 * g2) + 9;
 #pragma unroll
     for (int b2 = 0; b2 < 3; ++b2) {
-      const double g0 = fg[9 + b2], g1 = fg[12 + b2], g2 = fg[15 + b2];
-      const double t1 = u[0] * g0 + u[4] * g1;
-      const double t0 = u[1] * g1 + u[3] * g2;
-      const double t2 = u[2] * g0;
-      const double e1 = dl0 * g0, e0 = dl1 * g1;
+      const double g0 = Gq[b2], g1v = Gq[3 + b2], g2v = Gq[6 + b2];
 #pragma unroll
       for (int b1 = 0; b1 < 3; ++b1) {
         double sacc = acc_mm[b1 + 3 * b2], dacc = acc_vm[b1 + 3 * b2];
-        sacc += fg[3 + b1] * t1;
-        sacc += fg[b1] * t0;
-        sacc += fg[6 + b1] * t2;
-        dacc += fg[3 + b1] * e1;
-        dacc += fg[b1] * e0;
+        sacc += g0 * X0[b1];
+        sacc += g1v * X1[b1];
+        sacc += g2v * X2[b1];
+        dacc += g0 * Y0[b1];
+        dacc += g1v * Y1[b1];
         acc_mm[b1 + 3 * b2] = sacc; acc_vm[b1 + 3 * b2] = dacc;
       }
     }
@@ -958,15 +1017,15 @@ MAF_HD void phase_tangent_task(const Config& cfg, const TaskDesc& d, int t, cons
     return;
   }
   if (d.tr) {   // here `a` is the column node b
-    if (d.kind == 1) block_accumulate_tr<1, 2>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc);
-    else block_accumulate_tr<1, 3>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc);
+    if (d.kind == 1) block_accumulate_tr<1, 2>(A0, cfg.asize, ald, Phi, FG, d.c0, d.d0, a, acc);
+    else block_accumulate_tr<1, 3>(A0, cfg.asize, ald, Phi, FG, d.c0, d.d0, a, acc);
     scatter_col(cfg, fr, sink, a, I, J, rm, acc);
     return;
   }
   switch (d.kind) {
-    case 0: block_accumulate<1, 1, U>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc); break;
-    case 3: block_accumulate<2, 1, U>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc); break;
-    case 4: block_accumulate<2, 2, U>(A0, cfg.asize, ald, Phi, d.c0, d.d0, a, acc); break;
+    case 0: block_accumulate<1, 1, U>(A0, cfg.asize, ald, Phi, FG, d.c0, d.d0, a, acc); break;
+    case 3: block_accumulate<2, 1, U>(A0, cfg.asize, ald, Phi, FG, d.c0, d.d0, a, acc); break;
+    case 4: block_accumulate<2, 2, U>(A0, cfg.asize, ald, Phi, FG, d.c0, d.d0, a, acc); break;
     case 5: block_accumulate_mesh<3>(A0, cfg.asize, ald, boff, Phi, FG, G, d.c0, a, i, j, d.qterm, acc); break;
     case 6: block_accumulate_mesh<5>(A0, cfg.asize, ald, boff, Phi, FG, G, d.c0, a, i, j, d.qterm, acc); break;
     default: block_accumulate_mesh<6>(A0, cfg.asize, ald, boff, Phi, FG, G, d.c0, a, i, j, d.qterm, acc); break;
