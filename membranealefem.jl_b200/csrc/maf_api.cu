@@ -153,6 +153,41 @@ area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __
 #endif
 }
 
+// One-time (maf_create): the scatter map of every element, one CTA per element (maf_element.cuh::build_elslot).
+__global__ void __launch_bounds__(128)
+build_elslot_kernel(const Tables T, int32_t* __restrict__ elslot, int64_t* __restrict__ elbase, int* __restrict__ overflow) {
+  __shared__ long long s_col[72];
+  __shared__ long long s_base;
+  const int64_t el = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid < 72) s_col[tid] = T.nodecol[8 * (int64_t)T.IX[9 * el + (tid >> 3)] + (tid & 7)];
+  __syncthreads();
+  if (tid == 0) {
+    long long base = -1;
+    for (int k = 0; k < 72; ++k)
+      if (s_col[k] >= 0 && (base < 0 || s_col[k] < base)) base = s_col[k];
+    s_base = base < 0 ? 0 : base;
+    elbase[el] = s_base;
+  }
+  __syncthreads();
+  const long long base = s_base;
+  for (int k = tid; k < MAF_SLOT_INTS; k += 128) {
+    int32_t v = -1;
+    if (k < 729) {
+      const int b = k / 81, a = (k % 81) / 9, J = k % 9;
+      if (J < 8) {
+        const long long c = s_col[8 * b + J];
+        if (c >= 0) {
+          const long long off = c - base + T.pairoff[(int64_t)T.elpair[81 * el + 9 * a + b] * 8 + J];
+          if (off > 0x7fffff00LL) *overflow = 1;
+          v = (int32_t)off;
+        }
+      }
+    }
+    elslot[(size_t)MAF_SLOT_INTS * el + k] = v;
+  }
+}
+
 __global__ void __launch_bounds__(128)
 boundary_kernel(const __grid_constant__ Config cfg, const Tables T, const BoundaryTables BT, int bc, double fval,
                 double dt, const double* __restrict__ xms, double* __restrict__ r_gl, double* __restrict__ nzval,
@@ -619,6 +654,20 @@ int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* pa
     h->T.nodemask32 = upload(h, M.nodemask32.data(), M.nodemask32.size());
     h->T.utab = M.utab.empty() ? nullptr : upload(h, M.utab.data(), M.utab.size());
     h->T.numnp = M.numnp; h->T.numel = M.numel; h->T.num1el = M.num1el; h->T.nuel1 = M.nuel1;
+    {   // per-element scatter maps, built on the device from the tables above (2.9 KB per element)
+      int32_t* d_slot = dalloc<int32_t>(h, (size_t)MAF_SLOT_INTS * M.numel);
+      int64_t* d_base = dalloc<int64_t>(h, (size_t)M.numel);
+      int* d_ovf = dalloc<int>(h, 1);
+      CU(cudaMemsetAsync(d_ovf, 0, sizeof(int), h->stream));
+      if (M.numel > 0) build_elslot_kernel<<<(unsigned)M.numel, 128, 0, h->stream>>>(h->T, d_slot, d_base, d_ovf);
+      CU(cudaGetLastError());
+      int ovf = 0;
+      CU(cudaMemcpyAsync(&ovf, d_ovf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      if (ovf) throw std::runtime_error("scatter map offset exceeds 32 bits (an element spans more than 2^31 stored entries)");
+      h->T.elslot = d_slot;
+      h->T.elbase = d_base;
+    }
     h->BT.edge1 = upload(h, M.edge1.data(), M.edge1.size());
     h->BT.edge2 = upload(h, M.edge2.data(), M.edge2.size());
     h->BT.elems = upload(h, M.b_elems.data(), M.b_elems.size());

@@ -39,10 +39,11 @@ inline const char* tuned_plan(int motion, int nchunks, int nwarps) {
 #ifdef MAF_NO_TUNED_PLAN
   return nullptr;
 #endif
-  // gains over the heuristic plan at 1001 x 1001 (gpurun_out/tune2_*.log of round 1)
-  if (motion == M_ALEVB && nchunks == 14) return "1,12,4/0,9/13,11,7,3,5/2,10,6,8";                // +3.7 %
-  if (motion == M_ALEV && nchunks == 17) return "10,13,15,1/2,16,12,14/3,5,11,6/0,4,9,8,7";        // +20 %
-  if (motion == M_EUL && nchunks == 16) return "7,6,9,10/8,13,3/5,4,2,15/14,12,0,1,11";            // +2.5 %
+  // gains over the heuristic plan at 1001 x 1001 (gpurun_out/tune3_*.log of round 1; the plans are retuned whenever
+  // the kernel changes -- the same plan lost 3 % when only the scatter map changed)
+  if (motion == M_ALEVB && nchunks == 14) return "1,10,12/0,9/13,11,4,6,5/2,7,8,3";                // +4.9 %
+  if (motion == M_ALEV && nchunks == 17) return "6,14,13,15,1/5,8,16/3,2,10,11/0,4,9,7,12";        // +6.5 % (+20 % over LPT)
+  if (motion == M_EUL && nchunks == 16) return "7,6,5,10/13,3,8/9,0,2,15/14,12,4,11,1";            // +5.8 %
   if (motion == M_LAG && nchunks == 6) return "1/2/0,4/3,5";                                       // +0.6 %
   return nullptr;
 }
@@ -333,8 +334,8 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   cfg.o_tdb = o; o += 82;
   cfg.o_int = o; o += (I_PAIR + 1) / 2;   // node ids, equation numbers, active-dof masks
   o += o & 1;
-  cfg.o_slot = o; o += 72;                // column pointers of (node b, dof J), int64
-  cfg.o_po = o; o += 81;
+  cfg.o_slot = o; o += MAF_SLOT_INTS / 2;  // scatter map of the element (int32, build_elslot)
+  cfg.o_po = o; o += 2;                    // its base (int64)
   o += o & 1;
   cfg.front_doubles = o;
   // back block (offsets relative to sm + 2 * front_doubles + 2 * MAF_IDS_DOUBLES: two ids buffers in between)
@@ -346,6 +347,23 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   cfg.o_A = o; o += 9 * cfg.asize;
   cfg.o_ctr = o; o += 2;
   cfg.smem_doubles = 2 * cfg.front_doubles + 2 * MAF_IDS_DOUBLES + o;
+  // interpolation table: E[gp][q] = sum_a Phi^{ch(q)}_a(gp) * (nodal values at o_src(q) + a); layout of E in
+  // maf_element.cuh (E_A, E_C, E_DV, E_V, E_DM, E_VM, E_LAM, E_PM)
+  for (int q = 0; q < 35; ++q) {
+    int src, ch;
+    if (q < 6) { ch = CH_N1 + q / 3; src = cfg.o_x + 9 * (q % 3); }
+    else if (q < 15) { ch = CH_N11 + (q - 6) / 3; src = cfg.o_x + 9 * ((q - 6) % 3); }
+    else if (q < 21) { ch = CH_N1 + (q - 15) / 3; src = cfg.o_cv + 9 * ((q - 15) % 3); }
+    else if (q < 24) { ch = CH_N; src = cfg.o_cv + 9 * (q - 21); }
+    else if (q < 30) { ch = CH_N1 + (q - 24) / 3; src = cfg.o_cm + 9 * ((q - 24) % 3); }
+    else if (q < 33) { ch = CH_N; src = cfg.o_cm + 9 * (q - 30); }
+    else if (q == 33) { ch = CH_N; src = cfg.o_cl; }
+    else { ch = CH_N; src = cfg.o_cp; }
+    cfg.interp_src[q] = (int16_t)src;
+    cfg.interp_fo[q] = (int8_t)ch_fo(ch);
+    cfg.interp_go[q] = (int8_t)ch_go(ch);
+  }
+
   // flattened task descriptors (need the final storage layout and rowmask)
   for (int k = 0; k < cfg.nblocks; ++k) {
     const Block& b = cfg.blocks[k];
@@ -376,7 +394,7 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   }
   // everything that is read with 16-byte loads must sit on an even double offset
   bool ok = !(cfg.o_A & 1) && !(cfg.o_phi & 1) && !(cfg.o_FG & 1) && !(cfg.asize & 1) &&
-            !(cfg.front_doubles & 1) && !(cfg.o_po & 1);
+            !(cfg.front_doubles & 1) && !(cfg.o_po & 1) && !(cfg.o_slot & 1);
   for (int f = 0; f < NFIELD; ++f) {
     ok = ok && !(cfg.aoff[f] & 1) && !(cfg.ald[f] & 1) && (cfg.bcol[f] < 0 || !(cfg.bcol[f] & 1));
     for (int g = 0; g < NFIELD; ++g)

@@ -112,6 +112,9 @@ struct Config {
   int item_rounds, task_rounds;
   int16_t item_slot[MAF_MAX_SLOTS];   // [round][tid] -> item id or -1
   int8_t chunk_slot[MAF_MAX_ROUNDS * 8];  // [round][warp] -> chunk id or -1
+  // interpolated field q of E: source of the nine nodal values, and the 1-D factors of its channel in FG
+  int16_t interp_src[35];
+  int8_t interp_fo[35], interp_go[35];
   uint8_t rowmask[8];             // per column dof J: bitmask of row dofs I whose block is in the pattern
   Material mat;
   double dbscale;                 // adb / zv
@@ -145,6 +148,8 @@ struct Tables {
   const int64_t* nodecol;   // numnp x 8: colptr[ID[J, node]], -1 for inactive dofs
   const int32_t* nodemask32;  // nodemask as int32 (the granularity of an asynchronous copy)
   const double* utab;       // (nuel1*nuel2) x BASIS_DOUBLES precomputed basis blocks, or NULL (built per element)
+  const int32_t* elslot;    // numel x MAF_SLOT_INTS: scatter map of every element (build_elslot), relative to elbase
+  const int64_t* elbase;    // numel: smallest column pointer among the element's active (node, dof) columns
   int64_t numnp, numel;
   int num1el, nuel1;
 };
@@ -246,7 +251,7 @@ MAF_HD void build_basis_block(int tid, int nt, const double* l1, const double* l
 //   level 1 (gather_ids_async)   node ids, pair ids, unique-element ids of element k + 2G -> ids buffer
 //   level 2 (gather_data_async)  nodal data, equation numbers, column pointers, pairoff rows, basis block of
 //                                element k + G (addresses from the ids buffer filled one iteration earlier)
-// ids buffer (int32): [0,9) node ids | [9,90) pair ids of (a,b) | 90, 91: unique-element id per direction
+// ids buffer (int32): [0,9) node ids | 9: element id | 90, 91: unique-element id per direction
 #define MAF_IDS_INTS 92
 #define MAF_IDS_DOUBLES 46
 MAF_HD void async_copy4(void* sdst, const void* gsrc) {
@@ -296,24 +301,53 @@ MAF_HD void gather_init(int tid, const Config& cfg, double* fr) {
 
 MAF_HD void gather_ids_async(int tid, const Tables& T, int64_t el, int32_t* ids) {
   if (tid < 9) async_copy4(ids + tid, T.IX + 9 * el + tid);
-  else if (tid < 90) async_copy4(ids + tid, T.elpair + 81 * el + (tid - 9));
+  else if (tid == 9) ids[9] = (int32_t)el;   // read by gather_data_async one iteration (and a barrier) later
   else if (tid == 90) async_copy4(ids + 90, T.uel1 + (el % T.num1el));
   else if (tid == 91) async_copy4(ids + 91, T.uel2 + (el / T.num1el));
 }
 
 // Work items k: [0,27) x | [27,99) control points (8 dof slots) | [99,108) active-dof mask | [108,180) equation
-// numbers | [180,252) column pointers of (node b, dof J) | [252,333) pairoff row of the node pair (a,b); then the
-// basis block Phi[gp][c][a2][4] | FG[gp][18] | w[9] | tdb of the (unique) element in 16-byte pieces.
-// Scatter map of the element, looked up once:
-//   slot(a, I; b, J) = col[8 b + J] + po[(9 a + b) * 8 + J] + rank(I | a, J)
-// col = column pointer of (b, J) (negative for a Dirichlet column), po = the pairoff row of the node pair (a, b).
-// (Folding col + po into one int32 table per element was measured: the extra pass costs what it saves.)
-#define MAF_GATHER_ITEMS 333
+// numbers; then the element's scatter map (MAF_SLOT_INTS int32 + its base) and the basis block
+// Phi[gp][c][a2][4] | FG[gp][18] | w[9] | tdb of the (unique) element in 16-byte pieces.
+// Scatter map of an element, precomputed once per mesh (build_elslot; 2.9 KB per element in HBM):
+//   slot(a, I; b, J) = elbase + elslot[81 b + 9 a + J] + rank(I | a, J),  elslot < 0 for a Dirichlet column
+// i.e. (column pointer of (b, J) - elbase) + (rows that precede node a's rows in that column). The scatter of an
+// entry is then one 32-bit shared-memory load, a compare and one 64-bit multiply-add in front of the reduction
+// (looking the column pointer and the pair offset up per entry cost 2.5 times the instructions; folding them per
+// element inside the kernel cost an extra pass that ate the gain).
+#define MAF_SLOT_INTS 732   // 81 * 9 = 729, padded to a multiple of four (16-byte copies)
+MAF_HD void build_elslot(const Tables& T, int64_t el, int32_t* out /* MAF_SLOT_INTS */, int64_t* base_out,
+                         int* overflow) {
+  int64_t base = -1;
+  for (int b = 0; b < 9; ++b) {
+    const int64_t nb = T.IX[9 * el + b];
+    for (int J = 0; J < 8; ++J) {
+      const int64_t c = T.nodecol[8 * nb + J];
+      if (c >= 0 && (base < 0 || c < base)) base = c;
+    }
+  }
+  if (base < 0) base = 0;
+  *base_out = base;
+  for (int k = 0; k < MAF_SLOT_INTS; ++k) {
+    int32_t v = -1;
+    if (k < 729) {
+      const int b = k / 81, a = (k % 81) / 9, J = k % 9;
+      if (J < 8) {
+        const int64_t c = T.nodecol[8 * (int64_t)T.IX[9 * el + b] + J];
+        if (c >= 0) {
+          const int64_t off = c - base + T.pairoff[(int64_t)T.elpair[81 * el + 9 * a + b] * 8 + J];
+          if (off > 0x7fffff00LL) *overflow = 1;
+          v = (int32_t)off;
+        }
+      }
+    }
+    out[k] = v;
+  }
+}
+#define MAF_GATHER_ITEMS 180
 MAF_HD void gather_data_async(int tid, const Config& cfg, const Tables& T, const int32_t* ids, const double* xms,
                               const double* cps, double* fr /* front block of the element */) {
   int32_t* si = reinterpret_cast<int32_t*>(fr + cfg.o_int);
-  long long* col = reinterpret_cast<long long*>(fr + cfg.o_slot);
-  unsigned long long* po = reinterpret_cast<unsigned long long*>(fr + cfg.o_po);
   const int64_t np = T.numnp;
   const int ndf = cfg.ndf;
 #pragma unroll
@@ -330,14 +364,17 @@ MAF_HD void gather_data_async(int tid, const Config& cfg, const Tables& T, const
       if (dof >= 0) async_copy8(fr + fb + 9 * i + a, cps + ids[a] + np * dof);
     } else if (k < 108) {
       async_copy4(si + I_MASK + (k - 99), T.nodemask32 + ids[k - 99]);
-    } else if (k < 180) {
+    } else if (k < MAF_GATHER_ITEMS) {
       const int a = (k - 108) >> 3, d = (k - 108) & 7;
       if (d < ndf) async_copy4(si + I_EQ + (k - 108), T.ID + (int64_t)ndf * ids[a] + d);
-    } else if (k < 252) {
-      async_copy8(col + (k - 180), T.nodecol + 8 * (int64_t)ids[(k - 180) >> 3] + ((k - 180) & 7));
-    } else if (k < MAF_GATHER_ITEMS) {
-      async_copy8(po + (k - 252), T.pairoff + (int64_t)ids[9 + (k - 252)] * 8);
     }
+  }
+  {
+    const int64_t el = ids[9];
+    const dbl2* src = reinterpret_cast<const dbl2*>(T.elslot + (size_t)MAF_SLOT_INTS * el);
+    dbl2* dst = reinterpret_cast<dbl2*>(fr + cfg.o_slot);
+    for (int k = tid; k < MAF_SLOT_INTS / 4; k += MAF_NT) async_copy16(dst + k, src + k);
+    if (tid == MAF_NT - 1) async_copy8(fr + cfg.o_po, T.elbase + el);
   }
   const int u1 = ids[90], u2 = ids[91];
   if (T.utab) {   // precomputed per unique element (the same products, formed once on the host): straight copy
@@ -361,28 +398,33 @@ MAF_HD void phase_interp(int tid, int nt, const Config& cfg, const double* fr, d
     for (int k = tid; k < 9 * cfg.asize / 2; k += nt) Az[k] = z;
     if (tid == 0) *reinterpret_cast<int*>(sm + cfg.o_ctr) = 0;   // chunk queue of the tangent phase
   }
-  for (int k = tid; k < 9 * 35; k += nt) {
-    const int gp = k / 35, q = k % 35;
-    int src, ch;
-    if (q < 6) { ch = CH_N1 + q / 3; src = cfg.o_x + 9 * (q % 3); }
-    else if (q < 15) { ch = CH_N11 + (q - 6) / 3; src = cfg.o_x + 9 * ((q - 6) % 3); }
-    else if (q < 21) { ch = CH_N1 + (q - 15) / 3; src = cfg.o_cv + 9 * ((q - 15) % 3); }
-    else if (q < 24) { ch = CH_N; src = cfg.o_cv + 9 * (q - 21); }
-    else if (q < 30) { ch = CH_N1 + (q - 24) / 3; src = cfg.o_cm + 9 * ((q - 24) % 3); }
-    else if (q < 33) { ch = CH_N; src = cfg.o_cm + 9 * (q - 30); }
-    else if (q == 33) { ch = CH_N; src = cfg.o_cl; }
-    else { ch = CH_N; src = cfg.o_cp; }
-    const double* ph = fr + cfg.o_phi + PHI_GP * gp + PHI_C * ch;
-    double s3[3];   // one partial sum per node row a2: three short dependency chains instead of one of nine
+  // One thread per (field q, Gauss row g2), sum-factorised over the tensor-product basis (gp = g1 + 3 g2,
+  // Phi^c_a = f^{o1}_{a1}(g1) g^{o2}_{a2}(g2)): T[a1] = sum_{a2} X[a1 + 3 a2] g_{a2}(g2), then E[g1] = sum_{a1} T[a1] f_{a1}(g1)
+  // -- the nine nodal values are read once for three Gauss points (21 instead of 54 shared-memory words per field
+  // and Gauss row), and the field's channel comes from a table instead of a chain of comparisons.
+  for (int k = tid; k < 3 * 35; k += nt) {
+    const int q = k / 3, g2 = k % 3;
+    const double* X = fr + cfg.interp_src[q];
+    const double* FG = fr + cfg.o_FG;
+    const double* gq = FG + FG_STRIDE * (3 * g2) + cfg.interp_go[q];
+    const double gv0 = gq[0], gv1 = gq[1], gv2 = gq[2];
+    double T[3];
 #pragma unroll
-    for (int a2 = 0; a2 < 3; ++a2) {
-      const dbl2 p01 = ld2(ph + 4 * a2);
-      const double p2 = ph[4 * a2 + 2];
-      s3[a2] = fr[src + 3 * a2] * p01.x;
-      s3[a2] += fr[src + 3 * a2 + 1] * p01.y;
-      s3[a2] += fr[src + 3 * a2 + 2] * p2;
+    for (int a1 = 0; a1 < 3; ++a1) {
+      double t = X[a1] * gv0;
+      t += X[a1 + 3] * gv1;
+      t += X[a1 + 6] * gv2;
+      T[a1] = t;
     }
-    sm[cfg.o_E + E_STRIDE * gp + q] = (s3[0] + s3[1]) + s3[2];
+    const int fo = cfg.interp_fo[q];
+#pragma unroll
+    for (int g1 = 0; g1 < 3; ++g1) {
+      const double* fq = FG + FG_STRIDE * g1 + fo;
+      double e = T[0] * fq[0];
+      e += T[1] * fq[1];
+      e += T[2] * fq[2];
+      sm[cfg.o_E + E_STRIDE * (g1 + 3 * g2) + q] = e;
+    }
   }
 }
 
@@ -937,23 +979,18 @@ MAF_HD void scatter_row(const Config& cfg, const double* fr, const KSink& sink, 
   const int32_t* si = reinterpret_cast<const int32_t*>(fr + cfg.o_int);
   const unsigned m = (unsigned)si[I_MASK + a];
   if (!((m >> I) & 1u)) return;   // rows of inactive dofs are discarded (FiniteElement.jl:107,129)
-  const long long* col = reinterpret_cast<const long long*>(fr + cfg.o_slot) + J;
-  const uint8_t* po8 = reinterpret_cast<const uint8_t*>(fr + cfg.o_po) + 72 * a + J;
-  double* dst = sink.nzval + popc8(m & rm & ((1u << I) - 1u));
-#if MAF_SCATTER_PRELOAD   // all slot look-ups first, then predicated reductions (measured: -2.6 %, more live registers)
-  long long cb[9];
-  int po[9];
-#pragma unroll
-  for (int b = 0; b < 9; ++b) { cb[b] = col[8 * b]; po[b] = po8[8 * b]; }
-#pragma unroll
-  for (int b = 0; b < 9; ++b) atomic_add_if(dst + (cb[b] + (long long)po[b]), acc[b], cb[b] >= 0);
-#else
+  const int32_t* sl = reinterpret_cast<const int32_t*>(fr + cfg.o_slot) + 9 * a + J;
+  const long long base = *reinterpret_cast<const long long*>(fr + cfg.o_po);
+  double* dst = sink.nzval + (base + popc8(m & rm & ((1u << I) - 1u)));
 #pragma unroll
   for (int b = 0; b < 9; ++b) {
-    const long long cb = col[8 * b];   // negative: columns exist only for active dofs (FiniteElement.jl:111)
-    if (cb >= 0) atomic_add(dst + (cb + (long long)po8[8 * b]), acc[b]);
-  }
+    const int off = sl[81 * b];   // negative: columns exist only for active dofs (FiniteElement.jl:111)
+#if MAF_SCATTER_PRELOAD
+    atomic_add_if(dst + off, acc[b], off >= 0);
+#else
+    if (off >= 0) atomic_add(dst + off, acc[b]);
 #endif
+  }
 }
 
 // scatter of the 9 entries of column (b, J) in the rows (a, I), a = 0..8 (transposed blocks)
@@ -965,26 +1002,16 @@ MAF_HD void scatter_col(const Config& cfg, const double* fr, const KSink& sink, 
     for (int a = 0; a < 9; ++a) dst[(size_t)(9 * a) * sink.nij] = acc[a];
     return;
   }
-  const long long cb = *(reinterpret_cast<const long long*>(fr + cfg.o_slot) + 8 * b + J);
-  if (cb < 0) return;   // columns exist only for active dofs (FiniteElement.jl:111)
+  const int32_t* sl = reinterpret_cast<const int32_t*>(fr + cfg.o_slot) + 81 * b + J;
+  if (sl[0] < 0) return;   // columns exist only for active dofs (FiniteElement.jl:111)
   const int32_t* si = reinterpret_cast<const int32_t*>(fr + cfg.o_int);
-  const uint8_t* po8 = reinterpret_cast<const uint8_t*>(fr + cfg.o_po) + 8 * b + J;
-  double* dst = sink.nzval + cb;
+  double* dst = sink.nzval + *reinterpret_cast<const long long*>(fr + cfg.o_po);
   const unsigned low = (1u << I) - 1u;
-#if MAF_SCATTER_PRELOAD
-  unsigned m[9];
-  int po[9];
-#pragma unroll
-  for (int a = 0; a < 9; ++a) { m[a] = (unsigned)si[I_MASK + a]; po[a] = po8[72 * a]; }
-#pragma unroll
-  for (int a = 0; a < 9; ++a) atomic_add_if(dst + (po[a] + popc8(m[a] & rm & low)), acc[a], (m[a] >> I) & 1u);
-#else
 #pragma unroll
   for (int a = 0; a < 9; ++a) {
     const unsigned m = (unsigned)si[I_MASK + a];
-    if ((m >> I) & 1u) atomic_add(dst + ((int)po8[72 * a] + popc8(m & rm & low)), acc[a]);
+    if ((m >> I) & 1u) atomic_add(dst + (sl[9 * a] + popc8(m & rm & low)), acc[a]);
   }
-#endif
 }
 
 // Gauss-point loop of the short blocks: three points per trip for ALE / LAG (measured +3 %); EUL loses 5 % with it

@@ -24,6 +24,8 @@ struct HostModel {
   std::vector<int32_t> IX0, ID0, uel1, uel2;
   std::vector<double> line1, line2, edge1, edge2, tdb, utab;
   std::vector<int64_t> nodecol;      // column pointers per (node, dof) (Tables)
+  std::vector<int32_t> elslot;       // per-element scatter maps, HOST copy: only built for the CPU emulation of the
+  std::vector<int64_t> elbase;       // kernels (tests/emu); the library builds them on the device (build_elslot_kernel)
   std::vector<int32_t> nodemask32;
   std::vector<int32_t> b_elems, b_offs, b_bdry, b_type;
   std::vector<double> b_val;
@@ -142,11 +144,23 @@ inline void build_host_model(HostModel& M, const maf_mesh_desc* d, const maf_par
 
 inline Tables host_tables(const HostModel& M) {
   Tables T;
+  T.elslot = M.elslot.empty() ? nullptr : M.elslot.data();
+  T.elbase = M.elbase.empty() ? nullptr : M.elbase.data();
   T.IX = M.IX0.data(); T.ID = M.ID0.data(); T.nodemask = M.sym.nodemask.data();
   T.uel1 = M.uel1.data(); T.uel2 = M.uel2.data(); T.line1 = M.line1.data(); T.line2 = M.line2.data();
   T.tdb = M.tdb.data(); T.colptr = M.sym.colptr.data(); T.elpair = M.sym.elpair.data();
   T.pairoff = M.sym.pairoff.data(); T.eq0 = M.sym.eq0.data(); T.nodecol = M.nodecol.data(); T.nodemask32 = M.nodemask32.data(); T.utab = M.utab.empty() ? nullptr : M.utab.data(); T.numnp = M.numnp; T.numel = M.numel; T.num1el = M.num1el; T.nuel1 = M.nuel1;
   return T;
+}
+// host copy of the per-element scatter maps (CPU emulation only; needs M.sym.elpair, i.e. before maf_create frees it)
+inline void build_host_elslot(HostModel& M) {
+  M.elslot.assign((size_t)MAF_SLOT_INTS * M.numel, -1);
+  M.elbase.assign((size_t)M.numel, 0);
+  Tables T = host_tables(M);
+  int overflow = 0;
+  for (int64_t e = 0; e < M.numel; ++e)
+    build_elslot(T, e, M.elslot.data() + (size_t)MAF_SLOT_INTS * e, M.elbase.data() + e, &overflow);
+  if (overflow) throw std::runtime_error("scatter map offset exceeds 32 bits");
 }
 inline BoundaryTables host_boundary_tables(const HostModel& M) {
   BoundaryTables B;

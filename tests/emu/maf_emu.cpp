@@ -85,6 +85,7 @@ void* emu_create(const maf_mesh_desc* d, const maf_params* p, int nthreads) {
   try {
     emu_model* m = new emu_model();
     build_host_model(m->M, d, p, nthreads);
+    build_host_elslot(m->M);
     return m;
   } catch (std::exception& e) {
     g_err = e.what();
