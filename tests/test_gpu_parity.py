@@ -188,3 +188,26 @@ def test_synthetic_large_patch_properties():
     fd = (rr[0] - rr[1]) / (2 * h)
     kd = K @ du
     assert np.abs(fd - kd).max() <= 1e-6 * np.abs(kd).max()
+
+
+def test_chunk_plan_override_changes_the_schedule_not_the_result(monkeypatch):
+    """MAF_PLAN replaces the static plan of the contraction phase (tools/tune_plan.py): any valid plan assembles the
+    same K (only the order of the atomic additions moves); an invalid one is refused by maf_create."""
+    p, hm, om, xms, cps, time, dt, args = make_case("alevb_pull_5x4")
+    asm = maf.Assembler(hm, p)
+    text = asm.chunk_plan()
+    warps = [[int(c) for c in w.split(",") if c] for w in text.split("/")]
+    assert sorted(c for w in warps for c in w) == list(range(sum(len(w) for w in warps)))
+    r0, nz0, _ = asm.assemble(xms, cps, time, dt, scatter_mode=maf.SCATTER_DETERMINISTIC)
+    # everything on the first warp, in reverse order
+    rev = ",".join(str(c) for c in sorted((c for w in warps for c in w), reverse=True))
+    monkeypatch.setenv("MAF_PLAN", rev)
+    asm2 = maf.Assembler(hm, p)
+    assert asm2.chunk_plan().split("/")[0] == rev
+    r1, nz1, _ = asm2.assemble(xms, cps, time, dt, scatter_mode=maf.SCATTER_DETERMINISTIC)
+    assert np.array_equal(nz0, nz1) and np.array_equal(r0, r1)   # deterministic path: bitwise
+    ra, nza, _ = asm2.assemble(xms, cps, time, dt, scatter_mode=maf.SCATTER_ATOMIC)
+    assert np.abs(nza - nz0).max() <= 1e-13 * np.abs(nz0).max()
+    monkeypatch.setenv("MAF_PLAN", "0,0,1")
+    with pytest.raises(maf.MafError, match="invalid chunk plan"):
+        maf.Assembler(hm, p)

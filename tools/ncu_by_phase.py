@@ -10,8 +10,8 @@ for l in open(sys.argv[2]):
     if m: cur = (m.group(1).split("/")[-1], int(m.group(2))); continue
     if re.match(r"\s+/\*[0-9a-f]{4,5}\*/", l): lines.append(cur)
 numel = float(sys.argv[3])
-R = [("gather", 240, 354), ("interp", 355, 395), ("gauss_item", 396, 628), ("residual", 629, 680), ("blk_short", 681, 738), ("blk_tr", 739, 786),
-     ("blk_mesh", 787, 849), ("blk_fused", 850, 926), ("scatter", 927, 998), ("task_setup", 999, 1048), ("phase_tangent", 1049, 1100)]
+R = [("gather", 240, 388), ("interp", 389, 429), ("gauss_item", 430, 662), ("residual", 663, 714), ("blk_short", 715, 772), ("blk_tr", 773, 820),
+     ("blk_mesh", 821, 883), ("blk_fused", 884, 960), ("scatter", 961, 1017), ("task_setup", 1018, 1067), ("phase_tangent", 1068, 1120)]
 def rng(f, ln):
     if f != "maf_element.cuh": return None
     for n, lo, hi in R:
