@@ -69,7 +69,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """Number of samples received so far (to cut the window of the timed region out of a longer recording)."""
+        return len(self.rows)
+
+    def stop(self, first=0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -79,7 +83,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+        for row in self.rows[first:]:
             f = [x.strip() for x in row.split(",")]
             if len(f) < 7:
                 continue
@@ -242,12 +246,15 @@ def run(a, out_stream):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        step()
-    barrier()
+    # the sampler needs ~0.1 s to deliver its first line: it is started before the warm-up and only the samples
+    # that arrive from the start of the timed region on are used
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    s_first = sampler.mark()
     l0 = asm.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms = []
@@ -266,8 +273,24 @@ def run(a, out_stream):
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
         launches = int(lt.item())
-    clocks = sampler.stop() if rank == 0 else None
     rnorm2 = float(d_n.item())
+    # a timed region shorter than the sampling period (many GPUs, few steps) may have seen no sample: keep the same
+    # load running, untimed, until two samples have arrived (every rank runs the same number of extra steps)
+    extra = 0
+    if world > 1:
+        need = torch.tensor([1 if (rank == 0 and sampler.mark() - s_first < 2) else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(need, 0)
+        short = bool(need.item())
+    else:
+        short = sampler.mark() - s_first < 2
+    if short:
+        for _ in range(int(max(1.0, 400.0 / max(ms / a.steps, 1e-3)))):   # ~0.4 s of the same steps
+            step()
+            extra += 1
+        barrier()
+    clocks = sampler.stop(s_first) if rank == 0 else None
+    if clocks is not None and extra:
+        clocks["note"] = f"timed region shorter than the sampling period: {extra} more untimed steps of the same load were sampled"
     value = mesh.numel * a.steps / (ms * 1e-3) / 1e6
 
     # ---- e2e through the host-buffer entry point (pinned host memory) ------------------------------------------
