@@ -136,7 +136,11 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
     cfg.aoff[f] = off;
     off += cfg.ncomp[f] * cfg.rnc[f] * ld;
   }
+  // per-Gauss-point stride of A: even (16-byte loads) and = 2 (mod 4), so that the stores of the Gauss-phase lanes,
+  // which write the same offset of different Gauss points, spread over 8 bank groups (328 doubles put them on 2,
+  // EUL's 320 on one: 9-way conflicts on every store of the phase)
   cfg.asize = off + (off & 1);
+  while (cfg.asize % 4 != 2) cfg.asize += 2;
 
   cfg.nblocks = (int)bl.size();
   for (int k = 0; k < cfg.nblocks; ++k) {
@@ -342,6 +346,7 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
   o = 0;
   cfg.o_E = o; o += 9 * E_STRIDE;
   cfg.o_S = o; o += 9 * S_STRIDE;
+  o += o & 1;
   cfg.o_G = o; o += 9 * G_STRIDE;
   o += o & 1;
   cfg.o_A = o; o += 9 * cfg.asize;

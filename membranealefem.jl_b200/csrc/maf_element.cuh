@@ -123,9 +123,11 @@ struct Config {
 };
 
 // interpolated Gauss-point inputs E[gp][.]
-enum { E_A = 0, E_C = 6, E_DV = 15, E_V = 21, E_DM = 24, E_VM = 30, E_LAM = 33, E_PM = 34, E_STRIDE = 36 };
+// (odd strides: the lanes of a Gauss-phase warp work on different Gauss points at the same offset -- with a stride
+// of 36 doubles their accesses fell on 4 bank groups, with 37 on 9)
+enum { E_A = 0, E_C = 6, E_DV = 15, E_V = 21, E_DM = 24, E_VM = 30, E_LAM = 33, E_PM = 34, E_STRIDE = 37 };
 // primal generalised stresses S[gp][.] : Sv[c][i] at 3c+i, Sm at 18+3c+i, Sl 36, Sp 37
-enum { S_V = 0, S_M = 18, S_L = 36, S_P = 37, S_STRIDE = 38 };
+enum { S_V = 0, S_M = 18, S_L = 36, S_P = 37, S_STRIDE = 39 };
 // integer scratch (int32 view of the o_int region)
 enum { I_NODE = 0, I_EQ = 9, I_MASK = 81, I_PAIR = 90, I_END = 171 };
 // per Gauss point geometry for the b-direction expansion: n[3], a^1[3], a^2[3], then w dt Q_k[i] (k-major)
