@@ -39,7 +39,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--motion", default="ALEVB", choices=["LAG", "EUL", "ALEV", "ALEVB"])
-    ap.add_argument("--n", type=int, default=1001, help="elements per direction of the synthetic patch")
+    ap.add_argument("--n", "--patch-n", type=int, default=int(os.environ.get("MAF_BENCH_N", "1001")),
+                    help="elements per direction of the synthetic patch (under torchrun use --patch-n or MAF_BENCH_N: "
+                         "torchrun's own parser rejects the abbreviation-like --n)")
     ap.add_argument("--scatter", default="atomic", choices=["atomic", "deterministic"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
