@@ -17,6 +17,7 @@ struct GatherTables {
   const int16_t* ij_of;      // 8 x 8: column of the (row dof I, col dof J) class in a staging row, -1 = no block
   uint8_t class_I[64], class_J[64];  // the classes in staging order (sorted by J, then I)
   int sym_fill;              // pattern holds rows without a class (MAF_PATTERN_SYM): they are written as zeros
+  int ncls;                  // number of classes (the staging rows are padded to an even stride nij >= ncls)
   int64_t npairs;
 };
 
@@ -44,9 +45,15 @@ MAF_HD void gather_K_pair(int64_t p, const Config& cfg, const Tables& T, const G
       if (T.IX[9 * e + k] == A) a = k;
     if (a < 0) continue;
     const double* row = kel + ((size_t)81 * (e - e0) + 9 * a + G.n2e_loc[q]) * nij;
+    // the stride nij is even and the rows are 16-byte aligned: two classes per load (the kernel is bound by the
+    // number of L1 accesses: 32 lanes read 32 different rows); a padding entry is read but never written back
 #pragma unroll
-    for (int c = 0; c < MAF_MAX_NIJ; ++c)
-      if (c < nij) acc[c] += row[c];
+    for (int c = 0; c < MAF_MAX_NIJ; c += 2)
+      if (c < nij) {
+        const dbl2 v = ld2(row + c);
+        acc[c] += v.x;
+        acc[c + 1] += v.y;
+      }
   }
   // classes are sorted by (J, I): walk them once, keeping the first slot of node A's rows in the current column
   int64_t colbase = 0;
@@ -54,7 +61,7 @@ MAF_HD void gather_K_pair(int64_t p, const Config& cfg, const Tables& T, const G
   bool colact = false;
 #pragma unroll
   for (int c = 0; c < MAF_MAX_NIJ; ++c) {
-    if (c >= nij) break;
+    if (c >= G.ncls) break;
     const int I = G.class_I[c], J = G.class_J[c];
     if (J != curJ) {
       curJ = J;

@@ -179,7 +179,9 @@ struct GatherHost {
   std::vector<int32_t> pair_node;
   std::vector<int16_t> ij_of;
   uint8_t class_I[64], class_J[64];
-  int nij = 0, sym_fill = 0;
+  int nij = 0;    // stride of a staging row in doubles: the class count rounded up to even (16-byte loads in the gather)
+  int ncls = 0;   // number of (row dof, col dof) classes
+  int sym_fill = 0;
 };
 inline void build_gather_host(const HostModel& M, GatherHost& GH) {
   const Symbolic& S = M.sym;
@@ -198,11 +200,14 @@ inline void build_gather_host(const HostModel& M, GatherHost& GH) {
         GH.class_J[GH.nij] = (uint8_t)J;
         GH.ij_of[8 * I + J] = (int16_t)GH.nij++;
       }
+  GH.ncls = GH.nij;
+  GH.nij += GH.nij & 1;
   GH.sym_fill = M.pattern_mode == MAF_PATTERN_SYM ? 1 : 0;
 }
 inline void fill_gather_tables(const GatherHost& GH, GatherTables& G) {
   for (int c = 0; c < 64; ++c) { G.class_I[c] = GH.class_I[c]; G.class_J[c] = GH.class_J[c]; }
   G.sym_fill = GH.sym_fill;
+  G.ncls = GH.ncls;
 }
 
 // processing order of the elements of a range: Z-order (Morton) over (e1, e2), so that the elements a wave of CTAs
