@@ -210,15 +210,14 @@ boundary_kernel(const __grid_constant__ Config cfg, const Tables T, const Bounda
   }
 }
 
-// Deterministic path (maf_gather.cuh): one thread per node pair / per residual row. (One warp per pair with
-// coalesced row reads was measured slower, 38.8 vs 25.3 ms: the per-pair index work is then done 32 times.)
+// Deterministic path (maf_gather.cuh): MAF_GATHER_LANES threads per node pair, one thread per residual row.
 __global__ void __launch_bounds__(128)
 gather_K_kernel(const __grid_constant__ Config cfg, const Tables T, const GatherTables G,
                 const double* __restrict__ kel, int nij, int64_t e0, int64_t e1, int64_t p_lo, int64_t p_hi,
                 double* __restrict__ nzval) {
-  for (int64_t p = p_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < p_hi;
-       p += (int64_t)gridDim.x * blockDim.x)
-    gather_K_pair(p, cfg, T, G, kel, nij, e0, e1, nzval);
+  const int64_t n = (p_hi - p_lo) * MAF_GATHER_LANES;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    gather_K_pair(p_lo + t / MAF_GATHER_LANES, (int)(t % MAF_GATHER_LANES), cfg, T, G, kel, nij, e0, e1, nzval);
 }
 __global__ void __launch_bounds__(128)
 gather_r_kernel(const __grid_constant__ Config cfg, const Tables T, const GatherTables G,

@@ -21,20 +21,27 @@ struct GatherTables {
   int64_t npairs;
 };
 
-// one node pair p = (A,B): the <= 8 x 8 dof block K[(A,:),(B,:)].
+// one node pair p = (A,B): the <= 8 x 8 dof block K[(A,:),(B,:)], summed by MAF_GATHER_LANES threads.
 // A staged row (element, a, b) holds the nij (row dof, col dof) classes contiguously, ordered by (J, I) -- the order
-// of the destination slots -- so the thread streams whole rows (16-byte loads) into registers and then writes the
-// active entries of every column in one pass.
+// of the destination slots -- padded to an even stride. Lane s of the pair owns the 16-byte chunks s, s + L, s + 2L, ...
+// of the row: the L lanes of a pair read 16 L contiguous bytes per load (the kernel is bound by the number of L1
+// accesses: with one thread per pair the 32 lanes of a warp read 32 different rows), keep <= 2 ceil(32 / L) sums in
+// registers and write their own classes. (One whole warp per pair was slower: the per-pair index work is then done 32
+// times.)
 #define MAF_MAX_NIJ 64
-MAF_HD void gather_K_pair(int64_t p, const Config& cfg, const Tables& T, const GatherTables& G, const double* kel,
-                          int nij, int64_t e0, int64_t e1, double* nzval) {
+#ifndef MAF_GATHER_LANES
+#define MAF_GATHER_LANES 8
+#endif
+MAF_HD void gather_K_pair(int64_t p, int s, const Config& cfg, const Tables& T, const GatherTables& G,
+                          const double* kel, int nij, int64_t e0, int64_t e1, double* nzval) {
+  constexpr int L = MAF_GATHER_LANES, NQ = (MAF_MAX_NIJ / 2 + L - 1) / L;
   const int ndf = cfg.ndf;
   const int32_t A = G.nbr[p], B = G.pair_node[p];
   const unsigned mA = T.nodemask[A], mB = T.nodemask[B];
   if (mA == 0 || mB == 0) return;
-  double acc[MAF_MAX_NIJ];
+  double acc[2 * NQ];
 #pragma unroll
-  for (int c = 0; c < MAF_MAX_NIJ; ++c) acc[c] = 0.0;
+  for (int c = 0; c < 2 * NQ; ++c) acc[c] = 0.0;
   // elements that contain both nodes, in ascending element id
   for (int64_t q = G.n2e_ptr[B]; q < G.n2e_ptr[B + 1]; ++q) {
     const int64_t e = G.n2e[q];
@@ -45,33 +52,29 @@ MAF_HD void gather_K_pair(int64_t p, const Config& cfg, const Tables& T, const G
       if (T.IX[9 * e + k] == A) a = k;
     if (a < 0) continue;
     const double* row = kel + ((size_t)81 * (e - e0) + 9 * a + G.n2e_loc[q]) * nij;
-    // the stride nij is even and the rows are 16-byte aligned: two classes per load (the kernel is bound by the
-    // number of L1 accesses: 32 lanes read 32 different rows); a padding entry is read but never written back
 #pragma unroll
-    for (int c = 0; c < MAF_MAX_NIJ; c += 2)
+    for (int k = 0; k < NQ; ++k) {
+      const int c = 2 * (s + L * k);   // a padding entry is read but never written back
       if (c < nij) {
         const dbl2 v = ld2(row + c);
-        acc[c] += v.x;
-        acc[c + 1] += v.y;
+        acc[2 * k] += v.x;
+        acc[2 * k + 1] += v.y;
       }
-  }
-  // classes are sorted by (J, I): walk them once, keeping the first slot of node A's rows in the current column
-  int64_t colbase = 0;
-  int curJ = -1;
-  bool colact = false;
-#pragma unroll
-  for (int c = 0; c < MAF_MAX_NIJ; ++c) {
-    if (c >= G.ncls) break;
-    const int I = G.class_I[c], J = G.class_J[c];
-    if (J != curJ) {
-      curJ = J;
-      colact = (mB >> J) & 1u;
-      if (colact) colbase = T.colptr[T.ID[(int64_t)ndf * B + J]] + T.pairoff[p * 8 + J];
     }
-    if (colact && ((mA >> I) & 1u)) nzval[colbase + popc8(mA & cfg.rowmask[J] & ((1u << I) - 1u))] = acc[c];
   }
+#pragma unroll
+  for (int k = 0; k < NQ; ++k)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = 2 * (s + L * k) + h;
+      if (c >= G.ncls) continue;
+      const int I = G.class_I[c], J = G.class_J[c];
+      if (!((mB >> J) & 1u) || !((mA >> I) & 1u)) continue;
+      const int64_t colbase = T.colptr[T.ID[(int64_t)ndf * B + J]] + T.pairoff[p * 8 + J];
+      nzval[colbase + popc8(mA & cfg.rowmask[J] & ((1u << I) - 1u))] = acc[2 * k + h];
+    }
   // P_sym pattern: rows of dof blocks that are identically zero are part of the pattern but own no class
-  if (G.sym_fill) {
+  if (G.sym_fill && s == 0) {
     for (int J = 0; J < ndf; ++J) {
       if (!((mB >> J) & 1u)) continue;
       const unsigned rows = mA & cfg.rowmask[J];

@@ -187,7 +187,8 @@ int emu_assemble(void* h, const double* xms, const double* cps, double time, dou
       G.n2e_ptr = M.sym.n2e_ptr.data(); G.n2e = M.sym.n2e.data(); G.n2e_loc = M.sym.n2e_loc.data();
       G.ij_of = GH.ij_of.data(); G.npairs = M.sym.npairs;
       fill_gather_tables(GH, G);
-      for (int64_t p = 0; p < G.npairs; ++p) gather_K_pair(p, M.cfg, T, G, kel.data(), GH.nij, e0, e1, nzval);
+      for (int64_t p = 0; p < G.npairs; ++p)
+        for (int s = 0; s < MAF_GATHER_LANES; ++s) gather_K_pair(p, s, M.cfg, T, G, kel.data(), GH.nij, e0, e1, nzval);
       for (int64_t k = 0; k < M.numnp * M.ndf; ++k) gather_r_row(k, M.cfg, T, G, rel.data(), e0, e1, r);
     }
     std::vector<double> sm(B_DOUBLES);
