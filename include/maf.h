@@ -177,6 +177,13 @@ int maf_assemble_resident(maf_handle* h, double time, double dt, double bend_tm,
  * (Analysis.jl:48). */
 int maf_elem_v_residuals(maf_handle* h, const int64_t* el_ids, int64_t n, double* rv);
 
+/* Page-lock / release a host buffer the caller owns (cudaHostRegister): maf_assemble copies from and into
+ * page-locked memory directly and at the full PCIe rate (pageable buffers work too, through staging copies). The
+ * outputs of calc_r_K have a fixed size per mesh (FiniteElement.jl:75-200 allocates them anew every call), so a host
+ * shim registers its r / nzval arrays once and reuses them. Errors: maf_last_error(NULL). */
+int maf_host_register(void* ptr, int64_t bytes);
+int maf_host_unregister(void* ptr);
+
 /* Measured FP64 FMA throughput of the device (TFLOP/s): the denominator of the FP64 roofline fraction. */
 int maf_fp64_peak(int device, double* tflops);
 

@@ -5,7 +5,7 @@ Layout:  csrc/   CUDA kernels (sm_100a) and the C ABI of include/maf.h  -> libme
          host/   Python mirror of the reference's Input/Analysis interface around the path
 """
 from .capi import (PATTERN_BLK, PATTERN_SYM, SCATTER_ATOMIC, SCATTER_DETERMINISTIC, Assembler, MafError,
-                   fp64_peak_tflops, load_library)
+                   fp64_peak_tflops, host_register, host_unregister, load_library)
 from .host.analysis import calc_r_K, run_analysis, time_step, update_xms
 from .host.api import restart, solve
 from .host.basis import (AreaGpBasisFns, BdryGpBasisFns, GaussPointsXi, GaussPointsZeta, LineGpBasisFns,

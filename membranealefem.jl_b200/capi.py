@@ -45,7 +45,7 @@ EXPORTS = ["maf_create", "maf_destroy", "maf_last_error", "maf_nnz", "maf_patter
            "maf_assemble_device", "maf_device_buffers", "maf_stream", "maf_sync", "maf_timings", "maf_launch_count",
            "maf_kernel_info", "maf_chunk_plan", "maf_set_element_range", "maf_range_info", "maf_fp64_peak",
            "maf_debug_phase_cycles", "maf_state_set", "maf_state_get", "maf_state_update", "maf_state_predict",
-           "maf_assemble_resident", "maf_elem_v_residuals"]
+           "maf_assemble_resident", "maf_elem_v_residuals", "maf_host_register", "maf_host_unregister"]
 
 
 def load_library(path=None):
@@ -75,6 +75,8 @@ def load_library(path=None):
     L.maf_launch_count.argtypes = [C.c_void_p, _I64P]
     L.maf_kernel_info.argtypes = [C.c_void_p, _I64P]
     L.maf_chunk_plan.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    L.maf_host_register.argtypes = [C.c_void_p, C.c_int64]
+    L.maf_host_unregister.argtypes = [C.c_void_p]
     L.maf_set_element_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     L.maf_range_info.argtypes = [C.c_void_p, _I64P]
     L.maf_fp64_peak.argtypes = [C.c_int, _F64P]
@@ -129,6 +131,20 @@ def make_mesh_desc(mesh, keep):
         d.bdry_elems[b - 1] = _ptr(arr, C.c_int64)
         d.bdry_count[b - 1] = len(arr)
     return d
+
+
+def host_register(arr, lib=None):
+    """Page-lock a numpy array the caller owns (maf_host_register): maf_assemble then copies from / into it directly
+    at the full PCIe rate. Pair with host_unregister before the array is freed."""
+    L = lib or load_library()
+    if L.maf_host_register(arr.ctypes.data_as(C.c_void_p), arr.nbytes) != 0:
+        raise MafError(L.maf_last_error(None).decode())
+
+
+def host_unregister(arr, lib=None):
+    L = lib or load_library()
+    if L.maf_host_unregister(arr.ctypes.data_as(C.c_void_p)) != 0:
+        raise MafError(L.maf_last_error(None).decode())
 
 
 class Assembler:

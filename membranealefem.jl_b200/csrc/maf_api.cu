@@ -1121,4 +1121,30 @@ int maf_fp64_peak(int device, double* tflops) {
   }
 }
 
+int maf_host_register(void* ptr, int64_t bytes) {
+  try {
+    if (!ptr || bytes <= 0) throw std::runtime_error("null buffer");
+    CU(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return 0;
+  } catch (std::exception& e) {
+    cudaGetLastError();   // a refused registration is not sticky: do not leave it for the next launch check
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_create_err = e.what();
+    return 2;
+  }
+}
+
+int maf_host_unregister(void* ptr) {
+  try {
+    if (!ptr) throw std::runtime_error("null buffer");
+    CU(cudaHostUnregister(ptr));
+    return 0;
+  } catch (std::exception& e) {
+    cudaGetLastError();
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_create_err = e.what();
+    return 2;
+  }
+}
+
 }  // extern "C"

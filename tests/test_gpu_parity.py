@@ -211,3 +211,22 @@ def test_chunk_plan_override_changes_the_schedule_not_the_result(monkeypatch):
     monkeypatch.setenv("MAF_PLAN", "0,0,1")
     with pytest.raises(maf.MafError, match="invalid chunk plan"):
         maf.Assembler(hm, p)
+
+
+def test_registered_host_buffers_give_the_same_result():
+    """maf_host_register / maf_host_unregister: outputs written into page-locked caller buffers equal the ones
+    written into pageable ones; a second registration of the same range is reported, not fatal."""
+    p, hm, om, xms, cps, time, dt, args = make_case("eul_pull_5x4")
+    asm = maf.Assembler(hm, p)
+    r0, nz0, rn0 = asm.assemble(xms, cps, time, dt, scatter_mode=maf.SCATTER_DETERMINISTIC)
+    r1, nz1 = np.full(asm.nmdf, np.nan), np.full(asm.nnz, np.nan)
+    maf.host_register(r1)
+    maf.host_register(nz1)
+    try:
+        with pytest.raises(maf.MafError):
+            maf.host_register(nz1)
+        asm.assemble(xms, cps, time, dt, scatter_mode=maf.SCATTER_DETERMINISTIC, r=r1, nzval=nz1)
+    finally:
+        maf.host_unregister(r1)
+        maf.host_unregister(nz1)
+    assert np.array_equal(r0, r1) and np.array_equal(nz0, nz1)
