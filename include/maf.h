@@ -101,6 +101,14 @@ const char* maf_last_error(const maf_handle* h);
 int maf_nnz(maf_handle* h, int64_t* nnz);
 int maf_pattern(maf_handle* h, int64_t* colptr, int64_t* rowval);
 
+/* The same pattern in pieces, for meshes whose full rowval (nnz Int64 values: 9.4 GB for the 10^6-element ALE patch)
+ * is more than a caller wants to hold at once -- a host that keeps K in column slices (one per GPU), or a spot check:
+ *   maf_colptr            colptr alone (nmdf+1, 1-based)
+ *   maf_pattern_columns   rowval of the columns [col_first, col_last] (1-based, inclusive):
+ *                         colptr[col_last+1] - colptr[col_first] values. */
+int maf_colptr(maf_handle* h, int64_t* colptr);
+int maf_pattern_columns(maf_handle* h, int64_t col_first, int64_t col_last, int64_t* rowval);
+
 /* The hot path with HOST buffers (what the Julia shim calls once per Newton iteration):
  *   xms  numnp x 3   column-major   (FiniteElement.jl:77)
  *   cps  numnp x ndf column-major   (FiniteElement.jl:78)
@@ -121,6 +129,11 @@ int maf_assemble_device(maf_handle* h, const double* d_xms, const double* d_cps,
 /* The handle's device buffers (xms: 3 numnp, cps: ndf numnp, r: nmdf, nzval: nnz, rnorm2: 1). */
 int maf_device_buffers(maf_handle* h, double** d_xms, double** d_cps, double** d_r, double** d_nzval,
                        double** d_rnorm2);
+/* Copy slices of the handle's own device results to the host after maf_assemble_device (blocking): rows
+ * [r_first, r_first + r_count) of r and entries [nz_first, nz_first + nz_count) of nzval, 1-based; a count of 0 skips
+ * that array. With maf_range_info this returns exactly what an element range has written. */
+int maf_download(maf_handle* h, int64_t r_first, int64_t r_count, double* r, int64_t nz_first, int64_t nz_count,
+                 double* nzval);
 /* The handle's stream (cudaStream_t) and a blocking wait on it. */
 int maf_stream(maf_handle* h, void** stream);
 int maf_sync(maf_handle* h);

@@ -45,7 +45,8 @@ EXPORTS = ["maf_create", "maf_destroy", "maf_last_error", "maf_nnz", "maf_patter
            "maf_assemble_device", "maf_device_buffers", "maf_stream", "maf_sync", "maf_timings", "maf_launch_count",
            "maf_kernel_info", "maf_chunk_plan", "maf_set_element_range", "maf_range_info", "maf_fp64_peak",
            "maf_debug_phase_cycles", "maf_state_set", "maf_state_get", "maf_state_update", "maf_state_predict",
-           "maf_assemble_resident", "maf_elem_v_residuals", "maf_host_register", "maf_host_unregister"]
+           "maf_assemble_resident", "maf_elem_v_residuals", "maf_host_register", "maf_host_unregister",
+           "maf_colptr", "maf_pattern_columns", "maf_download"]
 
 
 def load_library(path=None):
@@ -64,6 +65,9 @@ def load_library(path=None):
     L.maf_destroy.argtypes = [C.c_void_p]
     L.maf_nnz.argtypes = [C.c_void_p, _I64P]
     L.maf_pattern.argtypes = [C.c_void_p, _I64P, _I64P]
+    L.maf_colptr.argtypes = [C.c_void_p, _I64P]
+    L.maf_pattern_columns.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _I64P]
+    L.maf_download.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _F64P, C.c_int64, C.c_int64, _F64P]
     L.maf_assemble.argtypes = [C.c_void_p, _F64P, _F64P, C.c_double, C.c_double, C.c_double, C.c_int, _F64P, _F64P,
                                _F64P]
     L.maf_assemble_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
@@ -190,6 +194,27 @@ class Assembler:
             self._check(self.L.maf_pattern(self.h, _ptr(colptr, C.c_int64), _ptr(rowval, C.c_int64)))
             self._pattern = (colptr, rowval)
         return self._pattern
+
+    def colptr(self):
+        """colptr alone (1-based Int64, nmdf + 1)."""
+        colptr = np.empty(self.nmdf + 1, dtype=np.int64)
+        self._check(self.L.maf_colptr(self.h, _ptr(colptr, C.c_int64)))
+        return colptr
+
+    def pattern_columns(self, col_first, col_last, colptr=None):
+        """rowval (1-based) of the columns [col_first, col_last] only (maf_pattern_columns)."""
+        colptr = self.colptr() if colptr is None else colptr
+        n = int(colptr[col_last] - colptr[col_first - 1])
+        rowval = np.empty(n, dtype=np.int64)
+        self._check(self.L.maf_pattern_columns(self.h, col_first, col_last, _ptr(rowval, C.c_int64)))
+        return rowval
+
+    def download(self, r_first=1, r_count=0, nz_first=1, nz_count=0):
+        """Slices (1-based starts) of the handle's device-resident r / nzval after assemble_device."""
+        r, nz = np.empty(r_count), np.empty(nz_count)
+        self._check(self.L.maf_download(self.h, r_first, r_count, _ptr(r, C.c_double), nz_first, nz_count,
+                                        _ptr(nz, C.c_double)))
+        return r, nz
 
     def assemble(self, xms, cps, time, dt, bend_tm=1.0, scatter_mode=SCATTER_ATOMIC, r=None, nzval=None):
         """maf_assemble with host buffers: returns (r, nzval, sum(r^2))."""

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -747,6 +748,22 @@ int maf_pattern(maf_handle* h, int64_t* colptr, int64_t* rowval) {
   MAF_API_END(h)
 }
 
+int maf_colptr(maf_handle* h, int64_t* colptr) {
+  MAF_API_BEGIN(h)
+  if (!colptr) throw std::runtime_error("null output pointer");
+  for (int64_t c = 0; c <= h->M.nmdf; ++c) colptr[c] = h->M.sym.colptr[c] + 1;
+  MAF_API_END(h)
+}
+
+int maf_pattern_columns(maf_handle* h, int64_t col_first, int64_t col_last, int64_t* rowval) {
+  MAF_API_BEGIN(h)
+  if (!rowval) throw std::runtime_error("null output pointer");
+  if (col_first < 1 || col_last > h->M.nmdf || col_first > col_last + 1)
+    throw std::runtime_error("column range outside 1..nmdf");
+  build_rowval_columns(h->M.sym, h->M.ID0.data(), h->M.cfg.rowmask, col_first - 1, col_last, rowval);
+  MAF_API_END(h)
+}
+
 // is this host pointer page-locked (cudaMallocHost / cudaHostRegister)? then it can be copied from directly
 static bool is_pinned(const void* p) {
   cudaPointerAttributes at;
@@ -788,7 +805,11 @@ static void assemble_to_host(maf_handle* h, double time, double dt, double bend_
   cudaStream_t s = h->stream;
   const size_t br = sizeof(double) * (size_t)M.nmdf, bk = sizeof(double) * (size_t)M.sym.nnz;
   const bool full = h->e0 == 0 && h->e1 == M.numel;
-  const bool pipelined = scatter_mode == MAF_SCATTER_ATOMIC && full && M.numel >= 32768 && M.num2el >= 16;
+  // strips pay off once the device-to-host copy of nzval dominates; MAF_PIPELINE_MIN_ELEMS overrides the threshold
+  // (tests force the pipelined path on a small mesh with it)
+  int64_t min_elems = 32768;
+  if (const char* e = std::getenv("MAF_PIPELINE_MIN_ELEMS")) min_elems = std::atoll(e);
+  const bool pipelined = scatter_mode == MAF_SCATTER_ATOMIC && full && M.numel >= min_elems && M.num2el >= 16;
   if (!pipelined) {
     do_assemble_device(h, h->d_xms, h->d_cps, time, dt, bend_tm, scatter_mode, h->d_r, h->d_nz,
                        rnorm2 ? h->d_rn : nullptr, s, true);
@@ -976,6 +997,23 @@ int maf_device_buffers(maf_handle* h, double** d_xms, double** d_cps, double** d
   if (d_r) *d_r = h->d_r;
   if (d_nzval) *d_nzval = h->d_nz;
   if (d_rnorm2) *d_rnorm2 = h->d_rn;
+  MAF_API_END(h)
+}
+
+int maf_download(maf_handle* h, int64_t r_first, int64_t r_count, double* r, int64_t nz_first, int64_t nz_count,
+                 double* nzval) {
+  MAF_API_BEGIN(h)
+  const HostModel& M = h->M;
+  if (r_count < 0 || nz_count < 0) throw std::runtime_error("negative count");
+  if (r_count > 0 && (!r || r_first < 1 || r_first + r_count - 1 > M.nmdf)) throw std::runtime_error("row range outside 1..nmdf");
+  if (nz_count > 0 && (!nzval || nz_first < 1 || nz_first + nz_count - 1 > M.sym.nnz))
+    throw std::runtime_error("entry range outside 1..nnz");
+  if (r_count > 0)
+    CU(cudaMemcpyAsync(r, h->d_r + (r_first - 1), sizeof(double) * (size_t)r_count, cudaMemcpyDeviceToHost, h->stream));
+  if (nz_count > 0)
+    CU(cudaMemcpyAsync(nzval, h->d_nz + (nz_first - 1), sizeof(double) * (size_t)nz_count, cudaMemcpyDeviceToHost,
+                       h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   MAF_API_END(h)
 }
 

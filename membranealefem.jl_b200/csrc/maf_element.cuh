@@ -621,7 +621,9 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const 
         const int d = CH_N1 + mu;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          const double Pij = (i == j ? 1.0 : 0.0) - g.n[i] * g.n[j];
+          // tangential projector delta_ij - n_i n_j, formed as a^mu_i a_mu_j: no cancellation of two O(1) terms, and
+          // exactly zero where the reference's complex step gives an exact zero (flat patch, i = j = z)
+          const double Pij = g.up[0][i] * a[0][j] + g.up[1][i] * a[1][j];
 #pragma unroll
           for (int al = 0; al < 2; ++al)
             put(cfg, Agp, F_V, i, CH_N1 + al, F_V, j, d, wJ * zv * (g.up[al][j] * g.up[mu][i] + Aup[mu][al] * Pij));

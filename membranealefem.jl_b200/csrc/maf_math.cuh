@@ -271,6 +271,13 @@ MAF_HD void bdry_eval(const TA a[2][3], int bdry, int ntype, double fval /* nval
   // tau = +-a_1 or +-a_2, normalised: BOTTOM +a1, RIGHT +a2, TOP -a1, LEFT -a2 (:438-448)
   const int al = (bdry == 1 || bdry == 3) ? 0 : 1;
   const double sgn = (bdry == 1 || bdry == 2) ? 1.0 : -1.0;
+  // The reference normalises tau with dot(tau, tau), which CONJUGATES (FiniteElement.jl:448): its |tau| carries no
+  // complex-step derivative, whereas `inorm` below is differentiated. The results coincide because every Neumann type
+  // multiplies by J_Gamma = 1 / |a^alpha . tau| (:372), which is homogeneous of degree -1 in tau: the scalar |tau|
+  // cancels in nu J_Gamma, tau J_Gamma and nu^alpha J_Gamma (STRETCH, SHEAR, MOMENT), exactly and for any
+  // perturbation. A future Neumann type that does not carry J_Gamma would need inorm's derivative frozen here; all
+  // three existing types are compared with the oracle (which conjugates like the reference) on all four sides in
+  // tests/test_truth_oracle.py and tests/test_gpu_parity.py::test_shear_and_top_bottom_moment.
   TA inorm = 1.0 / dsqrt(al == 0 ? a11 : a22);
   TA tau[3], nu[3];
 #pragma unroll

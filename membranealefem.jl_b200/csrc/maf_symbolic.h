@@ -166,4 +166,31 @@ inline void build_rowval(const Symbolic& S, const int32_t* ID0, const uint8_t ro
   });
 }
 
+// rows of the columns [c_lo, c_hi) only (0-based column range), written from rowval1[0]
+inline void build_rowval_columns(const Symbolic& S, const int32_t* ID0, const uint8_t rowmask[8], int64_t c_lo,
+                                 int64_t c_hi, int64_t* rowval1) {
+  const int ndf = S.ndf;
+  const int64_t base = S.colptr[c_lo];
+  // unknowns are numbered node-major: eq0 (first active equation at or after a node) is monotone, so the nodes that
+  // own the columns [c_lo, c_hi) are a contiguous range
+  int64_t n_lo = std::lower_bound(S.eq0.begin(), S.eq0.end(), (int32_t)c_lo) - S.eq0.begin();
+  int64_t n_hi = std::lower_bound(S.eq0.begin(), S.eq0.end(), (int32_t)c_hi) - S.eq0.begin();
+  n_lo = std::max<int64_t>(0, n_lo - 1);
+  n_hi = std::min<int64_t>(S.numnp, n_hi + 1);
+  parallel_for(n_hi - n_lo, [&](int64_t lo, int64_t hi) {
+    for (int64_t B = n_lo + lo; B < n_lo + hi; ++B)
+      for (int J = 0; J < ndf; ++J) {
+        const int32_t eq = ID0[(int64_t)ndf * B + J];
+        if (eq < c_lo || eq >= c_hi) continue;
+        int64_t k = S.colptr[eq] - base;
+        for (int64_t p = S.nbr_ptr[B]; p < S.nbr_ptr[B + 1]; ++p) {
+          const int32_t A = S.nbr[p];
+          const unsigned m = S.nodemask[A] & rowmask[J];
+          for (int I = 0; I < ndf; ++I)
+            if ((m >> I) & 1u) rowval1[k++] = (int64_t)ID0[(int64_t)ndf * A + I] + 1;
+        }
+      }
+  });
+}
+
 }  // namespace maf

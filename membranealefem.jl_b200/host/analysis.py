@@ -21,12 +21,20 @@ from .pullforce import calc_pull_force, get_adj_maps, get_pull_el_id
 
 
 def _assembler(mesh, p, args):
-    key = (id(p), args.get("pattern_mode", PATTERN_BLK))
+    """One library handle per (parameters, pattern mode, device), kept on the mesh. Keyed by the VALUE of the frozen
+    Params (an `id` is reused after garbage collection; the handle bakes in kb, kg, zv, pn, adb, am and the motion)."""
+    key = (p, args.get("pattern_mode", PATTERN_BLK), args.get("device", -1))
     cache = mesh.__dict__.setdefault("_assemblers", {})
     if key not in cache:
         cache[key] = Assembler(mesh, p, pattern_mode=args.get("pattern_mode", PATTERN_BLK),
                                device=args.get("device", -1))
     return cache[key]
+
+
+def close_assemblers(mesh):
+    """Release every cached handle of this mesh (each holds the device copies of the tables, r and nzval)."""
+    for asm in mesh.__dict__.pop("_assemblers", {}).values():
+        asm.close()
 
 
 def calc_r_K(mesh, xms, cps, time, dt, p, **args):
@@ -126,7 +134,8 @@ def run_analysis(mesh, xms, cps, p, **args):
     if pull:   # pull force local mappings (Analysis.jl:46-56)
         assert all(get_v_order(mesh.dofs)), "f_pull needs 3-D velocity"
         adj_el_ids, adj_node_map = get_adj_maps(mesh.num1el, mesh.numel, mesh.IX, p.poly)
-        if out and not args.get("append", False):
+        append = "in_path" in args and args["out_path"] == args["in_path"]       # Analysis.jl:34
+        if out and not append:
             with open(os.path.join(args["out_path"], "f-pull.txt"), "a") as f:
                 f.write("time\txp\typ\tzp\tfx\tfy\tfz\n")
     f_pulls = args.get("f_pulls")

@@ -30,7 +30,10 @@ def solve(p, **args):
 
 def restart(p_file, a_file, **r_args):
     """MembraneAleFem.restart(p_file, a_file; r_args...) (MembraneAleFem.jl:75-107): reload the serialised
-    parameters and arguments, overlay the new keyword arguments and re-enter `solve`."""
+    parameters and arguments, overlay the new keyword arguments and re-enter `solve`.
+
+    params.dat / args.dat are pickles (the reference uses Julia's Serialization the same way): loading them executes
+    whatever they contain, so only files this package wrote itself (`_display_params`) may be passed in."""
     with open(p_file, "rb") as f:
         p = pickle.load(f)
     with open(a_file, "rb") as f:

@@ -13,7 +13,16 @@ import dataclasses
 
 
 def strip_rows(num2el, world, rank):
-    """Element rows [r0, r1) of strip `rank`."""
+    """Element rows [r0, r1) of strip `rank`.
+
+    Every strip must hold at least TWO element rows: a quadratic strip touches node rows e2 .. e2 + 2, so with a
+    single-row strip rank k and rank k + 2 would share a node row and the exchange -- which only talks to the ranks
+    k - 1 and k + 1 -- would silently drop that overlap (and an empty strip has no range at all)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside 0..{world - 1}")
+    if world > 1 and num2el // world < 2:
+        raise ValueError(f"{num2el} element rows cannot be cut into {world} strips of at least 2 rows: "
+                         "use fewer ranks (the interface exchange only couples neighbouring strips)")
     return (rank * num2el) // world, ((rank + 1) * num2el) // world
 
 

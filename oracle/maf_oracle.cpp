@@ -32,7 +32,116 @@
 #include <unordered_map>
 #include <vector>
 
+// Two kinds of build of this ONE source (oracle/Makefile):
+//   libmaf_oracle.so  real_t = double, cd = std::complex<double>: the restated reference algorithm.
+//   libmaf_truth.so   -DORC_TRUTH=1 (long double, 64-bit mantissa) / libmaf_truthq.so -DORC_TRUTH=2 (__float128,
+//                     113 bits): the very same algorithm, operation for operation, evaluated in extended precision
+//                     on the same double inputs and rounded to double at the very end. It measures how far a double
+//                     evaluation (this oracle, the GPU kernels) is from the exact value of the reference's formulas.
+//                     Every number additionally carries E, the first-order running bound of the rounding error the
+//                     REFERENCE ALGORITHM ITSELF commits in double precision, in units of eps (Wilkinson forward
+//                     analysis, one rounding per operation):
+//                         z = x +- y : E(z) = E(x) + E(y) + |z|          z = x * y : E(z) = |x| E(y) + |y| E(x) + |z|
+//                         z = x / y  : E(z) = E(x)/|y| + |x| E(y)/y^2 + |z|      z = sqrt(x) : E(z) = E(x)/(2 z) + |z|
+//                     (inputs are exact doubles, E = 0). E is what "sum of |terms|" means once the cancellations
+//                     inside the terms are counted too; the parity rule's floor is a multiple of eps * E per entry.
+#if defined(ORC_TRUTH)
+#if ORC_TRUTH == 2
+typedef __float128 real_t;
+// sqrt without libquadmath: long-double estimate, two Newton steps (64 -> 128 -> 256 correct bits, rounded to 113)
+static inline real_t r_sqrt(real_t x) {
+  if (!(x > 0)) return 0;
+  real_t y = (real_t)sqrtl((long double)x);
+  y = (y + x / y) / 2;
+  y = (y + x / y) / 2;
+  return y;
+}
+#else
+typedef long double real_t;
+static inline real_t r_sqrt(real_t x) { return sqrtl(x); }
+#endif
+static inline real_t r_abs(real_t x) { return x < 0 ? -x : x; }
+struct cd {   // complex number over real_t, plain formulas (what -fcx-limited-range gives std::complex), + error bounds
+  real_t re, im, er, ei;
+  cd() : re(0), im(0), er(0), ei(0) {}
+  cd(real_t r) : re(r), im(0), er(0), ei(0) {}
+  cd(double r) : re(r), im(0), er(0), ei(0) {}
+  cd(int r) : re(r), im(0), er(0), ei(0) {}
+  cd(real_t r, real_t i) : re(r), im(i), er(0), ei(0) {}
+  cd(real_t r, real_t i, real_t a, real_t b) : re(r), im(i), er(a), ei(b) {}
+  real_t real() const { return re; }
+  real_t imag() const { return im; }
+  cd& operator+=(const cd& o);
+  cd& operator-=(const cd& o);
+  cd& operator/=(const cd& o);
+};
+static inline cd operator+(const cd& a, const cd& b) {
+  const real_t r = a.re + b.re, i = a.im + b.im;
+  return cd(r, i, a.er + b.er + r_abs(r), a.ei + b.ei + r_abs(i));
+}
+static inline cd operator-(const cd& a, const cd& b) {
+  const real_t r = a.re - b.re, i = a.im - b.im;
+  return cd(r, i, a.er + b.er + r_abs(r), a.ei + b.ei + r_abs(i));
+}
+static inline cd operator-(const cd& a) { return cd(-a.re, -a.im, a.er, a.ei); }
+static inline cd operator*(const cd& a, const cd& b) {
+  const real_t ar = r_abs(a.re), ai = r_abs(a.im), br = r_abs(b.re), bi = r_abs(b.im);
+  const real_t r = a.re * b.re - a.im * b.im, i = a.re * b.im + a.im * b.re;
+  // each product: |x| E(y) + |y| E(x) + |x y|; then the sum / difference
+  const real_t e_rr = ar * b.er + br * a.er + ar * br, e_ii = ai * b.ei + bi * a.ei + ai * bi;
+  const real_t e_ri = ar * b.ei + bi * a.er + ar * bi, e_ir = ai * b.er + br * a.ei + ai * br;
+  return cd(r, i, e_rr + e_ii + r_abs(r), e_ri + e_ir + r_abs(i));
+}
+static inline cd operator/(const cd& a, const cd& b) {
+  // plain formula (a conj(b)) / |b|^2, analysed as it is evaluated
+  const real_t d = b.re * b.re + b.im * b.im;
+  const real_t br = r_abs(b.re), bi = r_abs(b.im);
+  const real_t e_d = 2 * br * b.er + br * br + 2 * bi * b.ei + bi * bi + d;
+  const cd num = a * cd(b.re, -b.im, b.er, b.ei);
+  const real_t r = num.re / d, i = num.im / d;
+  return cd(r, i, num.er / d + r_abs(num.re) * e_d / (d * d) + r_abs(r), num.ei / d + r_abs(num.im) * e_d / (d * d) + r_abs(i));
+}
+inline cd& cd::operator+=(const cd& o) { *this = *this + o; return *this; }
+inline cd& cd::operator-=(const cd& o) { *this = *this - o; return *this; }
+inline cd& cd::operator/=(const cd& o) { *this = *this / o; return *this; }
+#define ORC_MIXED(T)                                                                   \
+  static inline cd operator+(const cd& a, T b) { return a + cd((real_t)b); }          \
+  static inline cd operator+(T a, const cd& b) { return cd((real_t)a) + b; }          \
+  static inline cd operator-(const cd& a, T b) { return a - cd((real_t)b); }          \
+  static inline cd operator-(T a, const cd& b) { return cd((real_t)a) - b; }          \
+  static inline cd operator*(const cd& a, T b) { return a * cd((real_t)b); }          \
+  static inline cd operator*(T a, const cd& b) { return cd((real_t)a) * b; }          \
+  static inline cd operator/(const cd& a, T b) { return a / cd((real_t)b); }          \
+  static inline cd operator/(T a, const cd& b) { return cd((real_t)a) / b; }
+ORC_MIXED(double)
+ORC_MIXED(int)
+static inline cd c_conj(const cd& a) { return cd(a.re, -a.im, a.er, a.ei); }
+// principal square root. The path only takes roots of numbers with a positive real part and an O(eps_k) imaginary
+// part (metric determinants, squared lengths): sqrt(z) = (t, im / 2t), t = sqrt((|z| + re) / 2).
+static inline cd c_sqrt(const cd& z) {
+  const real_t m = r_sqrt(z.re * z.re + z.im * z.im);
+  if (z.re >= 0) {
+    const real_t t = r_sqrt((m + z.re) / 2);
+    if (t == 0) return cd(0.0);
+    const real_t i = z.im / (2 * t);
+    // first order in the (tiny) imaginary part: t ~ sqrt(re), im' ~ im / (2 sqrt(re))
+    const real_t e_t = z.er / (2 * t) + 3 * t;
+    return cd(t, i, e_t, z.ei / (2 * t) + r_abs(z.im) * e_t / (2 * t * t) + r_abs(i));
+  }
+  const real_t t = r_sqrt((m - z.re) / 2);
+  return cd(r_abs(z.im) / (2 * t), z.im < 0 ? -t : t, z.er / (2 * t) + 3 * t, z.er / (2 * t) + 3 * t);
+}
+static inline real_t c_er(const cd& z) { return z.er; }
+static inline real_t c_ei(const cd& z) { return z.ei; }
+#else
+typedef double real_t;
 typedef std::complex<double> cd;
+static inline real_t r_abs(real_t x) { return std::fabs(x); }
+static inline cd c_conj(const cd& a) { return std::conj(a); }
+static inline cd c_sqrt(const cd& z) { return std::sqrt(z); }
+static inline real_t c_er(const cd&) { return 0.0; }
+static inline real_t c_ei(const cd&) { return 0.0; }
+#endif
 
 // --- enums: src/input/Enums.jl:32-156, src/input/Dof.jl:28-33 -----------------
 enum Scenario { F_CAVI = 1, F_COUE = 2, F_POIS = 3, F_PULL = 4, F_BEND = 5 };
@@ -819,7 +928,7 @@ static void geo_dyn_stress(const cd* xms, const cd* cps, const int* dofs, const 
   g.acon[1][0] = -g.aco[1][0] * idet; g.acon[1][1] = g.aco[0][0] * idet;
   for (int al = 0; al < 2; ++al)
     for (int i = 0; i < 3; ++i) g.aup[al][i] = g.a_[0][i] * g.acon[0][al] + g.a_[1][i] * g.acon[1][al];
-  g.J = std::sqrt(det);
+  g.J = c_sqrt(det);
   for (int k = 0; k < 3; ++k)
     for (int mu = 0; mu < 2; ++mu) {
       g.Gam[k][mu] = 0;
@@ -1037,8 +1146,8 @@ static void calc_tau_nu(int bdry, const cd a_[2][3], const cd n[3], cd tau[3], c
     else tau[i] = -a_[1][i];
   }
   cd d = 0;  // dot(tau,tau) conjugates its first argument (:448)
-  for (int i = 0; i < 3; ++i) d += std::conj(tau[i]) * tau[i];
-  cd s = std::sqrt(d);
+  for (int i = 0; i < 3; ++i) d += c_conj(tau[i]) * tau[i];
+  cd s = c_sqrt(d);
   for (int i = 0; i < 3; ++i) tau[i] /= s;
   nu[0] = tau[1] * n[2] - tau[2] * n[1];
   nu[1] = tau[2] * n[0] - tau[0] * n[2];
@@ -1066,7 +1175,7 @@ static void calc_bdry_element_residual(const Mesh& m, int bdry, int ntype, doubl
       for (int i = 0; i < 3; ++i) t += g.aup[al][i] * tau[i];
       s2 += t * t;
     }
-    cd JG = 1.0 / std::sqrt(s2);
+    cd JG = 1.0 / c_sqrt(s2);
     if (ntype == STRETCH || ntype == SHEAR) {
       for (int a = 0; a < 9; ++a)
         for (int i = 0; i < 3; ++i) {
@@ -1097,9 +1206,11 @@ static void calc_bdry_element_residual(const Mesh& m, int bdry, int ntype, doubl
 
 // Element-level complex-step tangent shared by the area loop (FiniteElement.jl:100-126)
 // and the Neumann loop (:156-184). K_el is (9 ndf)^2 column-major.
+// r_mag / K_mag (may be NULL; zeros in the regular build): the error-bound scale E of every entry of r_el / K_el.
 template <class ResFn>
 static void elem_r_K(const Mesh& m, int64_t el, const double* xms_gl, const double* cps_gl, double dt,
-                     const int* mmo, ResFn&& res, std::vector<double>& r_el, std::vector<double>& K_el) {
+                     const int* mmo, ResFn&& res, std::vector<real_t>& r_el, std::vector<real_t>& K_el,
+                     std::vector<real_t>* r_mag = nullptr, std::vector<real_t>* K_mag = nullptr) {
   const int ndf = m.ndf, nd = NEN * ndf;
   const double ek = m.p.ek;
   std::vector<cd> xe(27), ce((size_t)9 * ndf), out(nd);
@@ -1112,6 +1223,11 @@ static void elem_r_K(const Mesh& m, int64_t el, const double* xms_gl, const doub
   r_el.assign(nd, 0.0);
   K_el.assign((size_t)nd * nd, 0.0);
   for (int i = 0; i < nd; ++i) r_el[i] = out[i].real();
+  if (K_mag) {
+    r_mag->assign(nd, 0.0);
+    K_mag->assign((size_t)nd * nd, 0.0);
+    for (int i = 0; i < nd; ++i) (*r_mag)[i] = c_er(out[i]);
+  }
   for (int a = 0; a < 9; ++a) {
     int64_t node = m.IX[(size_t)a + (size_t)NEN * (el - 1)];
     for (int d = 1; d <= ndf; ++d) {
@@ -1122,6 +1238,9 @@ static void elem_r_K(const Mesh& m, int64_t el, const double* xms_gl, const doub
       res(xe.data(), ce.data(), out.data());
       ce[a + 9 * (d - 1)] = save;
       for (int i = 0; i < nd; ++i) K_el[(size_t)i + (size_t)nd * col] += out[i].imag() / ek;
+      if (K_mag)   // the division by eps_k and the addition into K_el: one rounding each
+        for (int i = 0; i < nd; ++i)
+          (*K_mag)[(size_t)i + (size_t)nd * col] += (c_ei(out[i]) + 2 * r_abs(out[i].imag())) / ek;
       int comp = -1;
       for (int j = 0; j < 3; ++j)
         if (mmo[j] == d) { comp = j; break; }
@@ -1131,6 +1250,9 @@ static void elem_r_K(const Mesh& m, int64_t el, const double* xms_gl, const doub
         res(xe.data(), ce.data(), out.data());
         xe[a + 9 * comp] = sx;
         for (int i = 0; i < nd; ++i) K_el[(size_t)i + (size_t)nd * col] += (out[i].imag() / ek) * dt;
+        if (K_mag)
+          for (int i = 0; i < nd; ++i)
+            (*K_mag)[(size_t)i + (size_t)nd * col] += ((c_ei(out[i]) + 3 * r_abs(out[i].imag())) / ek) * r_abs((real_t)dt);
       }
     }
   }
@@ -1139,12 +1261,12 @@ static void elem_r_K(const Mesh& m, int64_t el, const double* xms_gl, const doub
 // Julia SparseMatrixCSC scalar `K[i,j] += v` semantics: an entry is created only when the value to store
 // is non-zero; once stored it stays stored (explicit zeros survive). Key = (col << 32) | row, 0-based.
 struct SpAcc {
-  std::unordered_map<uint64_t, double> m;
-  void add(int64_t row, int64_t col, double v) {
+  std::unordered_map<uint64_t, real_t> m;
+  void add(int64_t row, int64_t col, real_t v) {
     uint64_t key = ((uint64_t)col << 32) | (uint64_t)row;
     auto it = m.find(key);
     if (it == m.end()) {
-      double nv = 0.0 + v;
+      real_t nv = 0.0 + v;
       if (nv != 0.0) m.emplace(key, nv);
     } else it->second += v;
   }
@@ -1157,8 +1279,8 @@ struct Result {
 };
 
 struct FastAcc {  // accumulate into a caller-supplied 0-based CSC pattern (CPU-baseline mode)
-  const int64_t* colptr; const int64_t* rowval; std::vector<double> nz;
-  void add(int64_t row, int64_t col, double v) {
+  const int64_t* colptr; const int64_t* rowval; std::vector<real_t> nz;
+  void add(int64_t row, int64_t col, real_t v) {
     const int64_t* b = rowval + colptr[col];
     const int64_t* e = rowval + colptr[col + 1];
     const int64_t* it = std::lower_bound(b, e, row);
@@ -1169,22 +1291,27 @@ struct FastAcc {  // accumulate into a caller-supplied 0-based CSC pattern (CPU-
 // FiniteElement.jl:75-200
 template <class Acc>
 static void area_chunk(const Mesh& m, const double* xms, const double* cps, double dt, const int* mmo, int64_t e0,
-                       int64_t e1, std::vector<double>& r_th, Acc& K_th) {
+                       int64_t e1, std::vector<real_t>& r_th, Acc& K_th, std::vector<real_t>* rm_th = nullptr,
+                       Acc* Km_th = nullptr) {
   const int nd = NEN * m.ndf;
-  std::vector<double> r_el, K_el;
+  std::vector<real_t> r_el, K_el, rm_el, Km_el;
   std::vector<int> ids;
   for (int64_t el = e0; el <= e1; ++el) {
     elem_r_K(m, el, xms, cps, dt, mmo,
-             [&](const cd* xe, const cd* ce, cd* out) { calc_elem_residual(m, el, xe, ce, out); }, r_el, K_el);
+             [&](const cd* xe, const cd* ce, cd* out) { calc_elem_residual(m, el, xe, ce, out); }, r_el, K_el,
+             Km_th ? &rm_el : nullptr, Km_th ? &Km_el : nullptr);
     ids.clear();
     for (int i = 0; i < nd; ++i)
       if (m.LM[(size_t)i + (size_t)nd * (el - 1)] != 0) ids.push_back(i);
     for (int ri : ids) {
       int64_t gr = m.LM[(size_t)ri + (size_t)nd * (el - 1)];
       r_th[gr - 1] += r_el[ri];
+      if (Km_th) (*rm_th)[gr - 1] += rm_el[ri] + r_abs(r_el[ri]);   // + the rounding of the global addition
       for (int ci : ids) {
         int64_t gc = m.LM[(size_t)ci + (size_t)nd * (el - 1)];
         K_th.add(gr - 1, gc - 1, K_el[(size_t)ri + (size_t)nd * ci]);
+        if (Km_th)
+          Km_th->add(gr - 1, gc - 1, Km_el[(size_t)ri + (size_t)nd * ci] + r_abs(K_el[(size_t)ri + (size_t)nd * ci]));
       }
     }
   }
@@ -1192,9 +1319,10 @@ static void area_chunk(const Mesh& m, const double* xms, const double* cps, doub
 
 template <class Acc>
 static void neumann_loop(const Mesh& m, const double* xms, const double* cps, double time, double dt, const int* mmo,
-                         std::vector<double>& r_gl, Acc& K_gl) {
+                         std::vector<real_t>& r_gl, Acc& K_gl, std::vector<real_t>* rm_gl = nullptr,
+                         Acc* Km_gl = nullptr) {
   const int nd = NEN * m.ndf;
-  std::vector<double> r_el, K_el;
+  std::vector<real_t> r_el, K_el, rm_el, Km_el;
   std::vector<int> ids;
   for (const NeuBc& bc : m.inh_neu)
     for (int64_t el : m.bdry_elems[bc.bdry]) {
@@ -1202,16 +1330,19 @@ static void neumann_loop(const Mesh& m, const double* xms, const double* cps, do
                [&](const cd* xe, const cd* ce, cd* out) {
                  calc_bdry_element_residual(m, bc.bdry, bc.type, bc.val, el, xe, ce, time, out);
                },
-               r_el, K_el);
+               r_el, K_el, Km_gl ? &rm_el : nullptr, Km_gl ? &Km_el : nullptr);
       ids.clear();
       for (int i = 0; i < nd; ++i)
         if (m.LM[(size_t)i + (size_t)nd * (el - 1)] != 0) ids.push_back(i);
       for (int ri : ids) {
         int64_t gr = m.LM[(size_t)ri + (size_t)nd * (el - 1)];
         r_gl[gr - 1] += r_el[ri];
+        if (Km_gl) (*rm_gl)[gr - 1] += rm_el[ri] + r_abs(r_el[ri]);
         for (int ci : ids) {
           int64_t gc = m.LM[(size_t)ci + (size_t)nd * (el - 1)];
           K_gl.add(gr - 1, gc - 1, K_el[(size_t)ri + (size_t)nd * ci]);
+          if (Km_gl)
+            Km_gl->add(gr - 1, gc - 1, Km_el[(size_t)ri + (size_t)nd * ci] + r_abs(K_el[(size_t)ri + (size_t)nd * ci]));
         }
       }
     }
@@ -1231,7 +1362,7 @@ static Result* calc_r_K(const Mesh& m, const double* xms, const double* cps, dou
   get_m_motion_order(m.p.motion, m.dofs, mmo);
   auto chunks = make_chunks(m.numel, std::max(1, nthreads));
   const size_t nc = chunks.size();
-  std::vector<std::vector<double>> r_th(nc, std::vector<double>((size_t)m.nmdf, 0.0));
+  std::vector<std::vector<real_t>> r_th(nc, std::vector<real_t>((size_t)m.nmdf, 0.0));
   std::vector<SpAcc> K_th(nc);
   std::vector<std::thread> th;
   std::vector<std::string> errs(nc);
@@ -1243,7 +1374,7 @@ static Result* calc_r_K(const Mesh& m, const double* xms, const double* cps, dou
   for (auto& t : th) t.join();
   for (auto& e : errs) ORC_CHECK(e.empty(), e);
   // sum over tasks (:146-147): sparse `+` keeps only non-zero results
-  std::vector<double> r_gl = r_th[0];
+  std::vector<real_t> r_gl = r_th[0];
   SpAcc K_gl = std::move(K_th[0]);
   for (size_t c = 1; c < nc; ++c) {
     for (int64_t i = 0; i < m.nmdf; ++i) r_gl[i] += r_th[c][i];
@@ -1256,8 +1387,9 @@ static Result* calc_r_K(const Mesh& m, const double* xms, const double* cps, dou
   }
   neumann_loop(m, xms, cps, time, dt, mmo, r_gl, K_gl);
   Result* R = new Result();
-  R->r = r_gl;
-  std::vector<std::pair<uint64_t, double>> ent(K_gl.m.begin(), K_gl.m.end());
+  R->r.resize(r_gl.size());
+  for (size_t i = 0; i < r_gl.size(); ++i) R->r[i] = (double)r_gl[i];
+  std::vector<std::pair<uint64_t, real_t>> ent(K_gl.m.begin(), K_gl.m.end());
   std::sort(ent.begin(), ent.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
   R->colptr.assign((size_t)m.nmdf + 1, 0);
   R->rowval.resize(ent.size());
@@ -1266,7 +1398,7 @@ static Result* calc_r_K(const Mesh& m, const double* xms, const double* cps, dou
     int64_t col = (int64_t)(ent[k].first >> 32), row = (int64_t)(ent[k].first & 0xffffffffu);
     R->colptr[col + 1] += 1;
     R->rowval[k] = row + 1;
-    R->nzval[k] = ent[k].second;
+    R->nzval[k] = (double)ent[k].second;
   }
   R->colptr[0] = 1;
   for (int64_t c = 0; c < m.nmdf; ++c) R->colptr[c + 1] += R->colptr[c];
@@ -1276,28 +1408,42 @@ static Result* calc_r_K(const Mesh& m, const double* xms, const double* cps, dou
 // CPU-baseline mode: same element algorithm and threading scheme, accumulation into a given pattern.
 static void calc_r_K_fast(const Mesh& m, const double* xms, const double* cps, double time, double dt, int nthreads,
                           const int64_t* colptr0, const int64_t* rowval0, int64_t nnz, int64_t e_first,
-                          int64_t e_last, int with_neumann, double* r_out, double* nz_out) {
+                          int64_t e_last, int with_neumann, double* r_out, double* nz_out,
+                          double* rmag_out = nullptr, double* nzmag_out = nullptr) {
   int mmo[3];
   get_m_motion_order(m.p.motion, m.dofs, mmo);
   const int64_t ne = e_last - e_first + 1;
   auto chunks = make_chunks(ne, std::max(1, nthreads));
   const size_t nc = chunks.size();
-  std::vector<std::vector<double>> r_th(nc, std::vector<double>((size_t)m.nmdf, 0.0));
+  const bool want_mag = rmag_out || nzmag_out;   // truth builds only (the regular build accumulates zeros)
+  std::vector<std::vector<real_t>> r_th(nc, std::vector<real_t>((size_t)m.nmdf, 0.0));
   std::vector<FastAcc> K_th(nc);
   for (auto& k : K_th) { k.colptr = colptr0; k.rowval = rowval0; k.nz.assign((size_t)nnz, 0.0); }
+  std::vector<std::vector<real_t>> rm_th(want_mag ? nc : 0, std::vector<real_t>((size_t)m.nmdf, 0.0));
+  std::vector<FastAcc> Km_th(want_mag ? nc : 0);
+  for (auto& k : Km_th) { k.colptr = colptr0; k.rowval = rowval0; k.nz.assign((size_t)nnz, 0.0); }
   std::vector<std::thread> th;
   for (size_t c = 0; c < nc; ++c)
     th.emplace_back([&, c]() {
-      area_chunk(m, xms, cps, dt, mmo, e_first - 1 + chunks[c].first, e_first - 1 + chunks[c].second, r_th[c], K_th[c]);
+      area_chunk(m, xms, cps, dt, mmo, e_first - 1 + chunks[c].first, e_first - 1 + chunks[c].second, r_th[c], K_th[c],
+                 want_mag ? &rm_th[c] : nullptr, want_mag ? &Km_th[c] : nullptr);
     });
   for (auto& t : th) t.join();
   for (size_t c = 1; c < nc; ++c) {
     for (int64_t i = 0; i < m.nmdf; ++i) r_th[0][i] += r_th[c][i];
     for (int64_t i = 0; i < nnz; ++i) K_th[0].nz[i] += K_th[c].nz[i];
+    if (want_mag) {
+      for (int64_t i = 0; i < m.nmdf; ++i) rm_th[0][i] += rm_th[c][i];
+      for (int64_t i = 0; i < nnz; ++i) Km_th[0].nz[i] += Km_th[c].nz[i];
+    }
   }
-  if (with_neumann) neumann_loop(m, xms, cps, time, dt, mmo, r_th[0], K_th[0]);
-  if (r_out) std::memcpy(r_out, r_th[0].data(), sizeof(double) * (size_t)m.nmdf);
-  if (nz_out) std::memcpy(nz_out, K_th[0].nz.data(), sizeof(double) * (size_t)nnz);
+  if (with_neumann)
+    neumann_loop(m, xms, cps, time, dt, mmo, r_th[0], K_th[0], want_mag ? &rm_th[0] : nullptr,
+                 want_mag ? &Km_th[0] : nullptr);
+  if (r_out) for (int64_t i = 0; i < m.nmdf; ++i) r_out[i] = (double)r_th[0][i];
+  if (nz_out) for (int64_t i = 0; i < nnz; ++i) nz_out[i] = (double)K_th[0].nz[i];
+  if (rmag_out) for (int64_t i = 0; i < m.nmdf; ++i) rmag_out[i] = (double)rm_th[0][i];
+  if (nzmag_out) for (int64_t i = 0; i < nnz; ++i) nzmag_out[i] = (double)Km_th[0].nz[i];
 }
 
 // =============================================================================
@@ -1537,20 +1683,20 @@ void orc_geo_dyn_stress(void* h, int64_t el, int gp, const double* xms_el, const
   GDS g;
   geo_dyn_stress(xe.data(), ce.data(), m.dofs, f.N, f.dN, f.ddN, m.p.kb, m.p.kg, m.p.zv, g);
   int k = 0;
-  for (int i = 0; i < 3; ++i) o[k++] = g.x[i].real();
-  for (int al = 0; al < 2; ++al) for (int i = 0; i < 3; ++i) o[k++] = g.a_[al][i].real();
-  for (int be = 0; be < 2; ++be) for (int al = 0; al < 2; ++al) o[k++] = g.acon[al][be].real();
-  for (int be = 0; be < 2; ++be) for (int al = 0; al < 2; ++al) o[k++] = g.aco[al][be].real();
-  o[k++] = g.J.real();
-  for (int i = 0; i < 3; ++i) o[k++] = g.n[i].real();
-  for (int be = 0; be < 2; ++be) for (int al = 0; al < 2; ++al) o[k++] = g.b[al][be].real();
-  o[k++] = g.H.real(); o[k++] = g.K.real();
-  for (int i = 0; i < 3; ++i) o[k++] = g.sig[i].real();
-  for (int i = 0; i < 3; ++i) o[k++] = g.sigm[i].real();
-  for (int i = 0; i < 3; ++i) o[k++] = g.M[i].real();
-  o[k++] = g.lam.real(); o[k++] = g.pm.real();
-  for (int i = 0; i < 3; ++i) o[k++] = g.v[i].real();
-  for (int i = 0; i < 3; ++i) o[k++] = g.vm[i].real();
+  for (int i = 0; i < 3; ++i) o[k++] = (double)g.x[i].real();
+  for (int al = 0; al < 2; ++al) for (int i = 0; i < 3; ++i) o[k++] = (double)g.a_[al][i].real();
+  for (int be = 0; be < 2; ++be) for (int al = 0; al < 2; ++al) o[k++] = (double)g.acon[al][be].real();
+  for (int be = 0; be < 2; ++be) for (int al = 0; al < 2; ++al) o[k++] = (double)g.aco[al][be].real();
+  o[k++] = (double)g.J.real();
+  for (int i = 0; i < 3; ++i) o[k++] = (double)g.n[i].real();
+  for (int be = 0; be < 2; ++be) for (int al = 0; al < 2; ++al) o[k++] = (double)g.b[al][be].real();
+  o[k++] = (double)g.H.real(); o[k++] = (double)g.K.real();
+  for (int i = 0; i < 3; ++i) o[k++] = (double)g.sig[i].real();
+  for (int i = 0; i < 3; ++i) o[k++] = (double)g.sigm[i].real();
+  for (int i = 0; i < 3; ++i) o[k++] = (double)g.M[i].real();
+  o[k++] = (double)g.lam.real(); o[k++] = (double)g.pm.real();
+  for (int i = 0; i < 3; ++i) o[k++] = (double)g.v[i].real();
+  for (int i = 0; i < 3; ++i) o[k++] = (double)g.vm[i].real();
 }
 
 // element-level r_el / K_el (area element), for fine-grained parity tests. K_el col-major (9ndf)^2.
@@ -1559,11 +1705,54 @@ int orc_elem_r_K(void* h, int64_t el, const double* xms, const double* cps, doub
   Mesh& m = *(Mesh*)h;
   int mmo[3];
   get_m_motion_order(m.p.motion, m.dofs, mmo);
-  std::vector<double> r, K;
+  std::vector<real_t> r, K;
   elem_r_K(m, el, xms, cps, dt, mmo,
            [&](const cd* xe, const cd* ce, cd* out) { calc_elem_residual(m, el, xe, ce, out); }, r, K);
-  std::copy(r.begin(), r.end(), r_el);
-  std::copy(K.begin(), K.end(), K_el);
+  for (size_t i = 0; i < r.size(); ++i) r_el[i] = (double)r[i];
+  for (size_t i = 0; i < K.size(); ++i) K_el[i] = (double)K[i];
+  return 0;
+  ORC_CATCH(1)
+}
+// same plus the error-bound scale E of every entry (zeros in the regular build); with bdry > 0 the Neumann boundary
+// element (bdry code, Neumann type, value) of element `el` instead of the area element (FiniteElement.jl:156-184)
+int orc_elem_r_K_mag(void* h, int64_t el, int bdry, int ntype, double nval, const double* xms, const double* cps,
+                     double time, double dt, double* r_el, double* K_el, double* r_mag, double* K_mag) {
+  ORC_TRY
+  Mesh& m = *(Mesh*)h;
+  int mmo[3];
+  get_m_motion_order(m.p.motion, m.dofs, mmo);
+  std::vector<real_t> r, K, rm, Km;
+  if (bdry > 0)
+    elem_r_K(m, el, xms, cps, dt, mmo,
+             [&](const cd* xe, const cd* ce, cd* out) {
+               calc_bdry_element_residual(m, bdry, ntype, nval, el, xe, ce, time, out);
+             }, r, K, &rm, &Km);
+  else
+    elem_r_K(m, el, xms, cps, dt, mmo,
+             [&](const cd* xe, const cd* ce, cd* out) { calc_elem_residual(m, el, xe, ce, out); }, r, K, &rm, &Km);
+  for (size_t i = 0; i < r.size(); ++i) { r_el[i] = (double)r[i]; if (r_mag) r_mag[i] = (double)rm[i]; }
+  for (size_t i = 0; i < K.size(); ++i) { K_el[i] = (double)K[i]; if (K_mag) K_mag[i] = (double)Km[i]; }
+  return 0;
+  ORC_CATCH(1)
+}
+// 0: regular oracle (double); 1: truth build in long double; 2: truth build in __float128
+int orc_truth_kind() {
+#if defined(ORC_TRUTH)
+  return ORC_TRUTH;
+#else
+  return 0;
+#endif
+}
+// replace the mesh's inhomogeneous Neumann conditions (tests of the SHEAR / TOP-BOTTOM MOMENT branches,
+// FiniteElement.jl:374-380, which no scenario of the reference's Bc.jl exercises)
+int orc_mesh_set_neumann(void* h, int n, const int32_t* bdry, const int32_t* type, const double* val) {
+  ORC_TRY
+  Mesh& m = *(Mesh*)h;
+  m.inh_neu.clear();
+  for (int k = 0; k < n; ++k) {
+    ORC_CHECK(bdry[k] >= 1 && bdry[k] <= 4 && type[k] >= 1 && type[k] <= 3, "bad Neumann condition");
+    m.inh_neu.push_back(NeuBc{bdry[k], type[k], val[k]});
+  }
   return 0;
   ORC_CATCH(1)
 }
@@ -1580,8 +1769,8 @@ int orc_elem_dof_residuals(void* h, int64_t el, const double* xms, const double*
   }
   cd v[27], mm[27], l[9], pp[9];
   calc_elem_dof_residuals(m, el, xe.data(), ce.data(), v, mm, l, pp);
-  for (int i = 0; i < 27; ++i) { rv[i] = v[i].real(); rm[i] = mm[i].real(); }
-  for (int i = 0; i < 9; ++i) { rl[i] = l[i].real(); rp[i] = pp[i].real(); }
+  for (int i = 0; i < 27; ++i) { rv[i] = (double)v[i].real(); rm[i] = (double)mm[i].real(); }
+  for (int i = 0; i < 9; ++i) { rl[i] = (double)l[i].real(); rp[i] = (double)pp[i].real(); }
   return 0;
   ORC_CATCH(1)
 }
@@ -1607,6 +1796,17 @@ int orc_calc_r_K_fast(void* h, const double* xms, const double* cps, double time
   ORC_TRY
   calc_r_K_fast(*(Mesh*)h, xms, cps, time, dt, nthreads, colptr0, rowval0, nnz, e_first, e_last, with_neumann, r_out,
                 nz_out);
+  return 0;
+  ORC_CATCH(1)
+}
+// same, plus the per-entry error-bound scale E on the same pattern (truth builds; zeros otherwise)
+int orc_calc_r_K_fast_mag(void* h, const double* xms, const double* cps, double time, double dt, int nthreads,
+                          const int64_t* colptr0, const int64_t* rowval0, int64_t nnz, int64_t e_first,
+                          int64_t e_last, int with_neumann, double* r_out, double* nz_out, double* rmag_out,
+                          double* nzmag_out) {
+  ORC_TRY
+  calc_r_K_fast(*(Mesh*)h, xms, cps, time, dt, nthreads, colptr0, rowval0, nnz, e_first, e_last, with_neumann, r_out,
+                nz_out, rmag_out, nzmag_out);
   return 0;
   ORC_CATCH(1)
 }

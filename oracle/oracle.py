@@ -26,25 +26,49 @@ class OrcParams(C.Structure):
                 ("pull_speed", C.c_double), ("bend_mf", C.c_double), ("bend_tm", C.c_double)]
 
 
-def build(force=False):
-    so = os.path.join(_HERE, "libmaf_oracle.so")
+# builds of the ONE source maf_oracle.cpp (oracle/Makefile):
+#   oracle  the restated reference algorithm in double / complex<double>
+#   truth   the same algorithm in long double (64-bit mantissa), + per-entry magnitudes sum |terms|
+#   truthq  the same in __float128 (113-bit mantissa): checks the long-double truth
+#   native  `oracle` compiled -O3 -march=native ON THIS MACHINE (bench.py's CPU baseline)
+_SO = {"oracle": "libmaf_oracle.so", "truth": "libmaf_truth.so", "truthq": "libmaf_truthq.so",
+       "native": "libmaf_oracle_native.so"}
+_LIBS = {}
+
+
+def _cpu_tag():
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+def build(force=False, kind="oracle"):
+    target = _SO[kind]
+    so = os.path.join(_HERE, target)
+    if kind == "native":      # keyed by the CPU it was compiled for: a copy made on another machine is not reused
+        so = os.path.join(_HERE, "libmaf_oracle_native_%s.so" % _cpu_tag())
     src = os.path.join(_HERE, "maf_oracle.cpp")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "libmaf_oracle.so"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", _HERE, "-B", target], stdout=subprocess.DEVNULL)
+        if kind == "native":
+            os.replace(os.path.join(_HERE, target), so)
     return so
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        L = C.CDLL(build())
+def lib(kind="oracle"):
+    if kind not in _LIBS:
+        L = C.CDLL(build(kind=kind))
         L.orc_last_error.restype = C.c_char_p
         for name in ("orc_mesh_create", "orc_kv_from_list", "orc_kv_uniform", "orc_kv_of_mesh", "orc_calc_r_K"):
             getattr(L, name).restype = C.c_void_p
         L.orc_result_nnz.restype = C.c_int64
         L.orc_mesh_bdry_count.restype = C.c_int64
-        _LIB = L
-    return _LIB
+        _LIBS[kind] = L
+    return _LIBS[kind]
 
 
 def _p(a, t=C.c_double):
@@ -194,35 +218,37 @@ class Mesh:
     """Oracle mesh (reference `Mesh(p; args...)`, src/input/Mesh.jl:48-80)."""
 
     def __init__(self, motion=ALEVB, scenario=F_PULL, num1el=17, num2el=17, length=64.0, kb=1.0, kg=-0.5, zv=1.0,
-                 pn=0.0, adb=None, am=1.0, ek=1e-15, pull_speed=0.0, bend_mf=0.0, bend_tm=1.0):
+                 pn=0.0, adb=None, am=1.0, ek=1e-15, pull_speed=0.0, bend_mf=0.0, bend_tm=1.0, kind="oracle"):
+        self.L = lib(kind)      # "oracle" (double), "truth" (long double), "truthq" (__float128), "native"
+        self.kind = kind
         adb = length ** 2 if adb is None else adb
         self.params = OrcParams(motion, scenario, num1el, num2el, length, kb, kg, zv, pn, adb, am, ek, pull_speed,
                                 bend_mf, bend_tm)
-        h = lib().orc_mesh_create(C.byref(self.params))
+        h = self.L.orc_mesh_create(C.byref(self.params))
         if not h:
-            raise AssertionError(_err())
+            raise AssertionError(self.L.orc_last_error().decode())
         self.h = C.c_void_p(h)
         s = np.empty(14, dtype=np.int64)
-        lib().orc_mesh_sizes(self.h, _p(s, C.c_int64))
+        self.L.orc_mesh_sizes(self.h, _p(s, C.c_int64))
         (self.numel, self.numnp, self.ndf, self.nmdf, self.num1el, self.num2el, self.num1np, self.num2np,
          self.nuel1, self.nuel2, self.n_dir, self.n_neu, self.nk1, self.nk2) = [int(v) for v in s]
         self.motion, self.scenario = motion, scenario
 
     def __del__(self):
         try:
-            lib().orc_mesh_destroy(self.h)
+            self.L.orc_mesh_destroy(self.h)
         except Exception:
             pass
 
     def _i64(self, fn, shape, *args):
         o = np.empty(int(np.prod(shape)), dtype=np.int64)
-        getattr(lib(), fn)(self.h, *args, _p(o, C.c_int64))
+        getattr(self.L, fn)(self.h, *args, _p(o, C.c_int64))
         return o.reshape(shape, order="F")
 
     @property
     def dofs(self):
         o = np.empty(8, dtype=np.int32)
-        lib().orc_mesh_dofs(self.h, _p(o, C.c_int32))
+        self.L.orc_mesh_dofs(self.h, _p(o, C.c_int32))
         return o
 
     @property
@@ -240,29 +266,29 @@ class Mesh:
     @property
     def ID_inv(self):
         n, d = np.empty(self.nmdf, dtype=np.int64), np.empty(self.nmdf, dtype=np.int64)
-        lib().orc_mesh_ID_inv(self.h, _p(n, C.c_int64), _p(d, C.c_int64))
+        self.L.orc_mesh_ID_inv(self.h, _p(n, C.c_int64), _p(d, C.c_int64))
         return n, d
 
     def kv(self, d):
-        return KnotVector(lib().orc_kv_of_mesh(self.h, d))
+        return KnotVector(self.L.orc_kv_of_mesh(self.h, d))
 
     def line(self, d):
         nel, nuel = (self.num1el, self.nuel1) if d == 1 else (self.num2el, self.nuel2)
         ids = np.empty(nel, dtype=np.int64)
         tab = np.empty((nuel, 3, 10))
         edge = np.empty((2, 10))
-        lib().orc_mesh_line(self.h, d, _p(ids, C.c_int64), _p(tab), _p(edge))
+        self.L.orc_mesh_line(self.h, d, _p(ids, C.c_int64), _p(tab), _p(edge))
         return ids, tab, edge
 
     def area_fns(self, el, gp):
         o = np.empty(55)
-        lib().orc_mesh_area_fns(self.h, C.c_int64(el), gp, _p(o))
+        self.L.orc_mesh_area_fns(self.h, C.c_int64(el), gp, _p(o))
         return {"w": o[0], "N": o[1:10].copy(), "dN": o[10:28].reshape(2, 9).T.copy(),
                 "ddN": o[28:55].reshape(3, 9).T.copy()}
 
     def bdry_fns(self, bdry, el, gp):
         o = np.empty(55)
-        if lib().orc_mesh_bdry_fns(self.h, bdry, C.c_int64(el), gp, _p(o)):
+        if self.L.orc_mesh_bdry_fns(self.h, bdry, C.c_int64(el), gp, _p(o)):
             raise AssertionError(_err())
         return {"w": o[0], "N": o[1:10].copy(), "dN": o[10:28].reshape(2, 9).T.copy(),
                 "ddN": o[28:55].reshape(3, 9).T.copy()}
@@ -272,22 +298,22 @@ class Mesh:
         return self._i64("orc_mesh_area_uel_ids", (self.numel,))
 
     def bdry_elems(self, bdry):
-        n = lib().orc_mesh_bdry_count(self.h, bdry)
+        n = self.L.orc_mesh_bdry_count(self.h, bdry)
         o = np.empty(n, dtype=np.int64)
-        lib().orc_mesh_bdry_elems(self.h, bdry, _p(o, C.c_int64))
+        self.L.orc_mesh_bdry_elems(self.h, bdry, _p(o, C.c_int64))
         return o
 
     def bdry_nodes(self, bdry):
         n = self.num1np if bdry in (BOTTOM, TOP) else self.num2np
         a, b = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
-        lib().orc_mesh_bdry_nodes(self.h, bdry, _p(a, C.c_int64), _p(b, C.c_int64))
+        self.L.orc_mesh_bdry_nodes(self.h, bdry, _p(a, C.c_int64), _p(b, C.c_int64))
         return a, b
 
     @property
     def bcs(self):
         du, dn, dv = np.empty(self.n_dir, np.int32), np.empty(self.n_dir, np.int64), np.empty(self.n_dir)
         nb, nt, nv = np.empty(self.n_neu, np.int32), np.empty(self.n_neu, np.int32), np.empty(self.n_neu)
-        lib().orc_mesh_bcs(self.h, _p(du, C.c_int32), _p(dn, C.c_int64), _p(dv), _p(nb, C.c_int32),
+        self.L.orc_mesh_bcs(self.h, _p(du, C.c_int32), _p(dn, C.c_int64), _p(dv), _p(nb, C.c_int32),
                            _p(nt, C.c_int32), _p(nv))
         return list(zip(du.tolist(), dn.tolist(), dv.tolist())), list(zip(nb.tolist(), nt.tolist(), nv.tolist()))
 
@@ -321,7 +347,7 @@ class Mesh:
         xe = np.asfortranarray(xms_el, dtype=np.float64)
         ce = np.asfortranarray(cps_el, dtype=np.float64)
         o = np.empty(44)
-        lib().orc_geo_dyn_stress(self.h, C.c_int64(el), gp, _p(xe), _p(ce), _p(o))
+        self.L.orc_geo_dyn_stress(self.h, C.c_int64(el), gp, _p(xe), _p(ce), _p(o))
         k = [0]
 
         def take(n, shape=None):
@@ -338,7 +364,7 @@ class Mesh:
         r, K = np.empty(nd), np.empty((nd, nd), order="F")
         xms = np.asfortranarray(xms, dtype=np.float64)
         cps = np.asfortranarray(cps, dtype=np.float64)
-        if lib().orc_elem_r_K(self.h, C.c_int64(el), _p(xms), _p(cps), C.c_double(dt), _p(r), _p(K)):
+        if self.L.orc_elem_r_K(self.h, C.c_int64(el), _p(xms), _p(cps), C.c_double(dt), _p(r), _p(K)):
             raise AssertionError(_err())
         return r, K
 
@@ -346,7 +372,7 @@ class Mesh:
         rv, rm, rl, rp = np.empty(27), np.empty(27), np.empty(9), np.empty(9)
         xms = np.asfortranarray(xms, dtype=np.float64)
         cps = np.asfortranarray(cps, dtype=np.float64)
-        if lib().orc_elem_dof_residuals(self.h, C.c_int64(el), _p(xms), _p(cps), _p(rv), _p(rm), _p(rl), _p(rp)):
+        if self.L.orc_elem_dof_residuals(self.h, C.c_int64(el), _p(xms), _p(cps), _p(rv), _p(rm), _p(rl), _p(rp)):
             raise AssertionError(_err())
         return rv, rm, rl, rp
 
@@ -375,17 +401,17 @@ class Mesh:
         import scipy.sparse as sp
         xms = np.asfortranarray(xms, dtype=np.float64)
         cps = np.asfortranarray(cps, dtype=np.float64)
-        res = lib().orc_calc_r_K(self.h, _p(xms), _p(cps), C.c_double(time), C.c_double(dt), nthreads)
+        res = self.L.orc_calc_r_K(self.h, _p(xms), _p(cps), C.c_double(time), C.c_double(dt), nthreads)
         if not res:
             raise AssertionError(_err())
         res = C.c_void_p(res)
-        nnz = lib().orc_result_nnz(res)
+        nnz = self.L.orc_result_nnz(res)
         r = np.empty(self.nmdf)
         colptr = np.empty(self.nmdf + 1, dtype=np.int64)
         rowval = np.empty(nnz, dtype=np.int64)
         nzval = np.empty(nnz)
-        lib().orc_result_get(res, _p(r), _p(colptr, C.c_int64), _p(rowval, C.c_int64), _p(nzval))
-        lib().orc_result_destroy(res)
+        self.L.orc_result_get(res, _p(r), _p(colptr, C.c_int64), _p(rowval, C.c_int64), _p(nzval))
+        self.L.orc_result_destroy(res)
         K = sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(self.nmdf, self.nmdf))
         return r, K
 
@@ -400,10 +426,49 @@ class Mesh:
         nnz = len(rowval0)
         r = np.empty(self.nmdf) if want_out else None
         nz = np.empty(nnz) if want_out else None
-        rc = lib().orc_calc_r_K_fast(self.h, _p(xms), _p(cps), C.c_double(time), C.c_double(dt), nthreads,
+        rc = self.L.orc_calc_r_K_fast(self.h, _p(xms), _p(cps), C.c_double(time), C.c_double(dt), nthreads,
                                      _p(colptr0, C.c_int64), _p(rowval0, C.c_int64), C.c_int64(nnz),
                                      C.c_int64(e_first), C.c_int64(e_last), int(with_neumann),
                                      _p(r) if want_out else None, _p(nz) if want_out else None)
         if rc:
             raise AssertionError(_err())
         return r, nz
+
+    # ---- extended-precision truth (kind="truth" / "truthq") and the untested Neumann branches ---------------
+    def set_neumann(self, conds):
+        """Replace mesh.inh_neu_bcs by [(bdry, type, value), ...] (tests of the SHEAR / TOP-BOTTOM MOMENT branches of
+        calc_bdry_element_residual, FiniteElement.jl:374-380, which no scenario in Bc.jl sets up)."""
+        nb = np.array([c[0] for c in conds], dtype=np.int32)
+        nt = np.array([c[1] for c in conds], dtype=np.int32)
+        nv = np.array([c[2] for c in conds], dtype=np.float64)
+        if self.L.orc_mesh_set_neumann(self.h, len(conds), _p(nb, C.c_int32), _p(nt, C.c_int32), _p(nv)):
+            raise AssertionError(self.L.orc_last_error().decode())
+        self.n_neu = len(conds)
+
+    def elem_r_K_mag(self, el, xms, cps, time, dt, bdry=0, ntype=0, nval=0.0):
+        """(r_el, K_el, r_mag, K_mag) of an area element (bdry = 0) or of the Neumann boundary element `el` of
+        boundary `bdry`; the magnitudes are sum |terms| per entry (zeros unless kind is "truth"/"truthq")."""
+        nd = 9 * self.ndf
+        r, K = np.empty(nd), np.empty((nd, nd), order="F")
+        rm, Km = np.empty(nd), np.empty((nd, nd), order="F")
+        xms = np.asfortranarray(xms, dtype=np.float64)
+        cps = np.asfortranarray(cps, dtype=np.float64)
+        if self.L.orc_elem_r_K_mag(self.h, C.c_int64(el), int(bdry), int(ntype), C.c_double(nval), _p(xms), _p(cps),
+                                   C.c_double(time), C.c_double(dt), _p(r), _p(K), _p(rm), _p(Km)):
+            raise AssertionError(self.L.orc_last_error().decode())
+        return r, K, rm, Km
+
+    def calc_r_K_on_pattern(self, xms, cps, time, dt, colptr0, rowval0, nthreads=1):
+        """r, nzval and the magnitudes sum |terms| (r_mag, nz_mag) accumulated into a given 0-based CSC pattern."""
+        xms = np.asfortranarray(xms, dtype=np.float64)
+        cps = np.asfortranarray(cps, dtype=np.float64)
+        colptr0 = np.ascontiguousarray(colptr0, dtype=np.int64)
+        rowval0 = np.ascontiguousarray(rowval0, dtype=np.int64)
+        nnz = len(rowval0)
+        r, nz, rm, nzm = np.empty(self.nmdf), np.empty(nnz), np.empty(self.nmdf), np.empty(nnz)
+        rc = self.L.orc_calc_r_K_fast_mag(self.h, _p(xms), _p(cps), C.c_double(time), C.c_double(dt), nthreads,
+                                          _p(colptr0, C.c_int64), _p(rowval0, C.c_int64), C.c_int64(nnz),
+                                          C.c_int64(1), C.c_int64(self.numel), 1, _p(r), _p(nz), _p(rm), _p(nzm))
+        if rc:
+            raise AssertionError(self.L.orc_last_error().decode())
+        return r, nz, rm, nzm

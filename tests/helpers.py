@@ -37,3 +37,31 @@ def P_of(m):
 
 
 MOTION_NAMES = {orc.STATIC: "STATIC", orc.EUL: "EUL", orc.LAG: "LAG", orc.ALEV: "ALEV", orc.ALEVB: "ALEVB"}
+
+
+def newton_history(assemble, motion, dofs, ID_inv, nmdf, xms, cps, dts, t0=0.0, enr=1e-12, solve=None):
+    """time_step! inside run_analysis! (FiniteElement.jl:11-63, Analysis.jl:60-93) around an arbitrary assembly:
+    `assemble(xms, cps, time, dt) -> (r, K)` (K scipy sparse). Mutates xms / cps; returns the eps = |du|_2 / nmdf of
+    every Newton iterate of every step."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import mafb200 as maf
+    n_inv, d_inv = ID_inv
+    hist, t = [], t0
+    for dt in dts:
+        t += dt
+        maf.update_xms(motion, xms, cps, dt, dofs)                  # predictor, Analysis.jl:70
+        eps = []
+        for it in range(14):                                        # iter < 15, FiniteElement.jl:29
+            r, K = assemble(xms, cps, t, dt)
+            du = -(solve(K, r) if solve else spla.splu(sp.csc_matrix(K)).solve(r))
+            dc = np.zeros_like(cps)
+            dc[n_inv - 1, d_inv - 1] = du
+            cps += dc
+            maf.update_xms(motion, xms, dc, dt, dofs)
+            eps.append(float(np.linalg.norm(du) / nmdf))
+            if eps[-1] < enr:
+                break
+        assert eps[-1] < enr, ("did not reach Newton-Raphson tolerance", t, eps)
+        hist.append(eps)
+    return hist

@@ -7,7 +7,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 import mafb200 as maf
-from cases import (DEFAULT_17, SMALL, active_unknowns, check_pattern_contract, compare, entrywise_rel_error,
+from cases import (DEFAULT_17, EXTRA_NEUMANN, SMALL, active_unknowns, check_pattern_contract, check_strict, compare,
                    make_case)
 
 pytestmark = pytest.mark.gpu
@@ -27,14 +27,37 @@ def test_assembly_matches_oracle(name):
     # DOF numbering / pattern container
     colptr, rowval = asm.pattern()
     assert colptr[0] == 1 and colptr[-1] == asm.nnz + 1 and rowval.min() >= 1 and rowval.max() <= hm.nmdf
+    truth = None
     for mode in (maf.SCATTER_ATOMIC, maf.SCATTER_DETERMINISTIC):
         r, nz, rn = asm.assemble(xms, cps, time, dt, bend_tm=args.get("bend_tm", 1.0), scatter_mode=mode)
         K = _K(asm, nz)
         er, ek = compare(r, K, r_o, K_o, active_unknowns(om, cps))
         assert er < RTOL and ek < RTOL, (name, mode, er, ek)
-        assert entrywise_rel_error(K, K_o) < RTOL
+        # strict rule on EVERY entry against the extended-precision truth (cases.strict_errors):
+        #   |x - truth| <= 1e-11 |truth| + eps E,  E = the reference algorithm's own rounding-error bound for that entry
+        uk, ur, truth = check_strict(name, r, nz, colptr, rowval, xms, cps, time, dt, f"gpu mode {mode}", truth)
         assert abs(rn - float(r @ r)) <= 1e-12 * max(float(r @ r), 1e-300)
         check_pattern_contract(K, K_o, generic="flat" not in name)
+    asm.close()
+
+
+@pytest.mark.parametrize("name", ["lag_bend_4x3", "alevb_bend_pn_4x3", "eul_bend_3x4"])
+def test_shear_and_top_bottom_moment(name):
+    """SHEAR on every side and MOMENT on TOP / BOTTOM (FiniteElement.jl:374-380; no scenario of Bc.jl sets them up):
+    injected through maf_mesh_desc.neu_* and the oracle's inh_neu_bcs, both scatter paths, oracle + strict rule."""
+    p, hm, om, xms, cps, time, dt, args = make_case(name)
+    hm.inh_neu_bcs = list(EXTRA_NEUMANN)
+    om.set_neumann(EXTRA_NEUMANN)
+    r_o, K_o = om.calc_r_K(xms, cps, time, dt)
+    asm = maf.Assembler(hm, p)
+    colptr, rowval = asm.pattern()
+    truth = None
+    for mode in (maf.SCATTER_ATOMIC, maf.SCATTER_DETERMINISTIC):
+        r, nz, _ = asm.assemble(xms, cps, time, dt, bend_tm=args.get("bend_tm", 1.0), scatter_mode=mode)
+        er, ek = compare(r, _K(asm, nz), r_o, K_o)
+        assert er < RTOL and ek < RTOL, (name, mode, er, ek)
+        _, _, truth = check_strict(name, r, nz, colptr, rowval, xms, cps, time, dt, f"gpu mode {mode}", truth,
+                                   neumann=EXTRA_NEUMANN)
     asm.close()
 
 
@@ -121,6 +144,82 @@ def test_newton_history_matches_oracle(motion):
             assert abs(eg - er_) <= 1e-6 * er_, (hist_gpu, hist_ref)
         assert hg[-1] < p.enr and hr[-1] < p.enr
     assert np.abs(xms - xo).max() <= 1e-9 and np.abs(cps - co).max() <= 1e-9
+
+
+def _load_newton_golden(name):
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"newton_17x17_{name}.npz"))
+    hist, k = [], 0
+    for n in z["lens"]:
+        hist.append(z["eps"][k:k + int(n)].tolist())
+        k += int(n)
+    return z, hist
+
+
+def _same_history(h_a, h_b, enr):
+    """Iterate by iterate: same number of iterations per step; every eps above the round-off level (1e-9: the last
+    iterate of a quadratically converging step is noise below enr = 1e-12) agrees to 1e-6 relative."""
+    assert [len(h) for h in h_a] == [len(h) for h in h_b], (h_a, h_b)
+    for ha, hb in zip(h_a, h_b):
+        for ea, eb in zip(ha, hb):
+            if eb > 1e-9:
+                assert abs(ea - eb) <= 1e-6 * eb, (ha, hb)
+            else:
+                assert ea < max(1e-9, 100 * eb) or ea < enr
+        assert ha[-1] < enr and hb[-1] < enr
+
+
+@pytest.mark.parametrize("name,motion", [("lag", maf.LAG), ("eul", maf.EUL), ("alevb", maf.ALEVB)])
+@pytest.mark.parametrize("resident", [False, True])
+def test_newton_history_17x17_32_steps(name, motion, resident):
+    """BASELINE.json configs 1-3 at the reference's own sizes: 17 x 17 patch, length 64, pull_speed 0.5,
+    dts = fill(0.5, 32) (docs/src/index.md:149-152, Params.jl:39-40). All 32 steps through the library (host loop and
+    device-resident loop) against the committed oracle-driven histories (tests/golden/make_newton_golden.py), plus a
+    fresh oracle run of the first 3 steps."""
+    from helpers import newton_history
+    from oracle import oracle as orc
+    p = maf.Params(motion=motion, scenario=maf.F_PULL, num1el=17, num2el=17, output=False)
+    args = dict(pull_speed=0.5, dts=[0.5] * 32, t0=0.0, t0_id=0)
+    mesh, xms, cps = maf.prepare_input(p, **args)
+    x0, c0 = xms.copy(), cps.copy()
+    hist = maf.run_analysis(mesh, xms, cps, p, resident=resident, **args)
+    z, hist_g = _load_newton_golden(name)
+    _same_history(hist, hist_g, p.enr)
+    assert np.abs(xms - z["xms"]).max() <= 1e-8 and np.abs(cps - z["cps"]).max() <= 1e-8
+    assert abs(xms[:, 2].max() - 8.0) < 1e-9          # the pulled nodes moved pull_speed * 16 (Bc.jl:228-243)
+    if not resident:
+        om = orc.Mesh(motion=int(motion), scenario=orc.F_PULL, num1el=17, num2el=17, pull_speed=0.5)
+        h3 = newton_history(lambda x, c, t, dt: om.calc_r_K(x, c, t, dt, nthreads=8), motion, mesh.dofs, om.ID_inv,
+                            om.nmdf, x0, c0, args["dts"][:3])
+        _same_history(hist[:3], h3, p.enr)
+    maf.pkg.host.analysis.close_assemblers(mesh)
+
+
+def test_headline_config_spot_parity():
+    """BASELINE.json config 5, the configuration the bench numbers are quoted on (1001 x 1001 F_PULL patch, centre-
+    refined knots = 625 unique elements, ALEVB, the bench's synthetic state): > 200 single elements -- the pulled
+    element and its two rings, corners, edges incl. the mid-edge Dirichlet nodes, the knot-spacing transitions, random
+    interior ones -- through maf_set_element_range(el, el) against the oracle's element routine scattered through LM
+    and against the extended-precision truth (tests/spot_parity.py). DOF numbering exact, every written slot inside
+    the element's LM x LM block, strict rule on every entry."""
+    import torch
+    from oracle import oracle as orc
+    from spot_parity import check_elements, select_elements
+    p = maf.Params(motion=maf.ALEVB, scenario=maf.F_PULL, num1el=1001, num2el=1001, output=False)
+    mesh = maf.Mesh(p, pull_speed=0.5)
+    xms, cps = maf.synthetic_state(mesh, p)
+    kw = dict(motion=orc.ALEVB, scenario=orc.F_PULL, num1el=1001, num2el=1001, length=p.length, pull_speed=0.5)
+    om, ot = orc.Mesh(**kw), orc.Mesh(kind="truth", **kw)
+    assert np.array_equal(om.ID, mesh.ID) and om.nmdf == mesh.nmdf and (om.nuel1, om.nuel2) == (25, 25)
+    asm = maf.Assembler(mesh, p)
+    dx = torch.from_numpy(np.ascontiguousarray(xms.T)).cuda()
+    dc = torch.from_numpy(np.ascontiguousarray(cps.T)).cuda()
+    els = select_elements(mesh)
+    assert len(els) >= 200
+    worst = check_elements(asm, mesh, om, ot, dx.data_ptr(), dc.data_ptr(), xms, cps, 0.5, 0.5, els)
+    print("headline spot parity:", worst)
+    assert worst["n"] == len(els) and worst["K_rel_oracle"] < RTOL
+    asm.close()
 
 
 def test_translate_ale_emulation():
@@ -230,3 +329,24 @@ def test_registered_host_buffers_give_the_same_result():
         maf.host_unregister(r1)
         maf.host_unregister(nz1)
     assert np.array_equal(r0, r1) and np.array_equal(nz0, nz1)
+
+
+def test_pipelined_host_path_on_a_small_mesh(monkeypatch):
+    """maf_assemble's strip-pipelined path (default from 32768 elements: finished nzval / r ranges are copied to the
+    host while the next strip of element rows is assembled) forced on a 17 x 17 mesh: bit-identical to the
+    deterministic path up to the order of the atomic additions, and within the strict rule of the truth."""
+    name = "alevb_pull_17x17"
+    p, hm, om, xms, cps, time, dt, args = make_case(name)
+    asm = maf.Assembler(hm, p)
+    colptr, rowval = asm.pattern()
+    r0, nz0, rn0 = asm.assemble(xms, cps, time, dt)
+    launches0 = asm.launch_count()
+    monkeypatch.setenv("MAF_PIPELINE_MIN_ELEMS", "1")
+    r1, nz1, rn1 = asm.assemble(xms, cps, time, dt)
+    assert asm.launch_count() - launches0 >= 8            # one area launch per strip: the pipelined path did run
+    assert np.abs(nz1 - nz0).max() <= 1e-13 * np.abs(nz0).max() and np.abs(r1 - r0).max() <= 1e-13 * np.abs(r0).max()
+    assert abs(rn1 - rn0) <= 1e-12 * rn0
+    check_strict(name, r1, nz1, colptr, rowval, xms, cps, time, dt, "pipelined host path")
+    rd, nzd, _ = asm.assemble_resident(time, dt)        # and through the resident entry point
+    assert np.abs(nzd - nz0).max() <= 1e-13 * np.abs(nz0).max()
+    asm.close()

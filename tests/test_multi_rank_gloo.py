@@ -96,6 +96,11 @@ def test_partition_arithmetic():
             assert a == nxt and b >= a
             nxt = b + 1
         assert nxt == 7 * n2 + 1
+    # strips thinner than two element rows would couple rank k with rank k + 2: refused, not mis-summed
+    for n2, world in [(4, 4), (3, 2), (5, 3), (2, 3)]:
+        with pytest.raises(ValueError, match="at least 2 rows"):
+            part.strip_rows(n2, world, 0)
+    assert part.strip_rows(4, 2, 1) == (2, 4) and part.strip_rows(1, 1, 0) == (0, 1)
     ranges = [(1, 100, 1, 1000), (81, 200, 801, 2000), (181, 300, 1801, 3000)]
     ov = part.overlaps(ranges, 1)
     assert [(o.peer, o.rows, o.slots) for o in ov] == [(0, slice(80, 100), slice(800, 1000)),
