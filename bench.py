@@ -11,6 +11,10 @@ N > 1 (torchrun): the patch is cut into N strips of element rows (strong scaling
 exchanges only the interface rows/entries with its neighbours over NCCL and the residual norm is all-reduced.
 --impl reference times the CPU restatement of the reference algorithm (the reference itself is Julia, which this
 image does not have) on a bounded sample of the same workload with all host threads.
+
+Process hygiene: the timed repo arm maps libmembrane_b200.so only; everything that needs the oracle -- the
+cpu_baseline leg, the CPU side of `newton_iteration`, the `parity_spot` check -- runs in child processes of this
+script (`--impl reference`, `--parity-spot`), and the reference arm never loads the product library.
 """
 import argparse
 import json
@@ -45,6 +49,12 @@ def parse():
     ap.add_argument("--scatter", default="atomic", choices=["atomic", "deterministic"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-newton", action="store_true", help="skip the newton_iteration object (configs 1-4)")
+    ap.add_argument("--no-spot", action="store_true", help="skip the parity_spot child process")
+    ap.add_argument("--parity-spot", action="store_true", help="child mode: single-element parity check on the bench "
+                    "patch against the oracle and the extended-precision truth; prints one JSON object")
+    ap.add_argument("--newton-cpu", action="store_true", help="with --impl reference: also time the CPU port on the "
+                    "17x17 meshes of configs 1-4 (for the newton_iteration object)")
     return ap.parse_args()
 
 
@@ -115,16 +125,21 @@ def lm_pattern(LM, nmdf):
     return np.cumsum(colptr), rows
 
 
+CPU_FLAGS = "g++ -O3 -march=native -ffp-contract=off -fcx-limited-range (oracle/Makefile: libmaf_oracle_native.so, " \
+            "compiled on this machine)"
+
+
 def cpu_reference_rate(motion, steps, warmup, target_s=1.5):
     """Times the oracle's calc_r_K (complex-step tangent, the reference's chunked threading scheme, private
-    accumulators, sum, serial Neumann loop -- FiniteElement.jl:75-200) on a bounded sample of the workload."""
+    accumulators, sum, serial Neumann loop -- FiniteElement.jl:75-200) on a bounded sample of the workload.
+    Inputs come from the pure-Python host mirror (mafb200 is imported, libmembrane_b200.so is NOT loaded)."""
     import mafb200 as maf
     from oracle import oracle as orc
     cores = os.cpu_count() or 1
     mcode = getattr(orc, motion)
 
     def setup(n):
-        om = orc.Mesh(motion=mcode, scenario=orc.F_PULL, num1el=n, num2el=n, pull_speed=0.5)
+        om = orc.Mesh(motion=mcode, scenario=orc.F_PULL, num1el=n, num2el=n, pull_speed=0.5, kind="native")
         p = maf.Params(motion=getattr(maf, motion), scenario=maf.F_PULL, num1el=n, num2el=n, output=False)
         hm = maf.Mesh(p, pull_speed=0.5)
         xms, cps = maf.synthetic_state(hm, p)
@@ -151,7 +166,125 @@ def cpu_reference_rate(motion, steps, warmup, target_s=1.5):
             "sample": f"{n}x{n}-element F_PULL {motion} patch ({om.numel} elements/step, {steps} steps, same "
                       f"perturbed state generator), C++ restatement of the reference algorithm (complex-step tangent, "
                       f"chunked std::thread tasks with private accumulators as FiniteElement.jl:88-147), "
-                      f"g++ -O2, {cores} threads; Julia itself is not installed"}, tot / steps * 1e3
+                      f"{CPU_FLAGS}, {cores} threads; Julia itself is not installed"}, tot / steps * 1e3
+
+
+NEWTON_CONFIGS = [("1 lag-pull", "LAG"), ("2 eul-pull", "EUL"), ("3 ale-pull", "ALEVB"), ("4 translate-ale", "ALEVB")]
+
+
+def newton_cpu_times():
+    """CPU port on the 17 x 17 meshes of BASELINE.json configs 1-4: ms per calc_r_K (all host threads, reference
+    threading scheme) on the deformed state after the predictor of step 1 -- the CPU side of `newton_iteration`."""
+    import mafb200 as maf
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    out = {}
+    for name, motion in NEWTON_CONFIGS:
+        p = maf.Params(motion=getattr(maf, motion), scenario=maf.F_PULL, num1el=17, num2el=17, output=False)
+        mesh, xms, cps = maf.prepare_input(p, pull_speed=0.5, dts=[0.5], t0=0.0, t0_id=0)
+        maf.update_xms(p.motion, xms, cps, 0.5, mesh.dofs)
+        om = orc.Mesh(motion=getattr(orc, motion), scenario=orc.F_PULL, num1el=17, num2el=17, pull_speed=0.5,
+                      kind="native")
+        ts = []
+        for _ in range(6):
+            t0 = time.perf_counter()
+            om.calc_r_K(xms, cps, 0.5, 0.5, nthreads=cores)
+            ts.append(time.perf_counter() - t0)
+        out[name] = {"cpu_port_assemble_ms": float(np.median(ts[1:]) * 1e3), "threads": cores}
+    return out
+
+
+def newton_gpu_times(maf, device):
+    """GPU side of `newton_iteration` (BASELINE.json metric, second half; loop of FiniteElement.jl:29-55): the four
+    small configs on the reference's default 17 x 17 mesh, two time steps each (pull_speed 0.5, dt 0.5). Per Newton
+    iteration: wall time of the assembly call through the C ABI with host buffers (maf_assemble: H2D state, kernels,
+    D2H r + nzval), of the device-resident variant (maf_assemble_resident: no state upload), the device time of the
+    kernels alone, and the host solve, timed separately (SciPy SuperLU stands in for Julia's UMFPACK `\\`): from
+    scratch in every iteration like the reference (:38), and through host/solver.py (value buffer owned by the solver,
+    column ordering chosen once per pattern)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    out = {}
+    for name, motion in NEWTON_CONFIGS:
+        p = maf.Params(motion=getattr(maf, motion), scenario=maf.F_PULL, num1el=17, num2el=17, output=False)
+        args = dict(pull_speed=0.5, dts=[0.5, 0.5], t0=0.0, t0_id=0, device=device)
+        mesh, xms, cps = maf.prepare_input(p, **args)
+        if name.startswith("4"):   # translate-ale emulation (SURVEY 8(d)4): converged tether state, then an in-plane
+            maf.run_analysis(mesh, xms, cps, p, **args)          # Dirichlet velocity on the pulled nodes
+            U = maf.Dof.Unknown
+            for (unk, node, val) in mesh.inh_dir_bcs:
+                cps[node - 1, mesh.dofs[U.vx] - 1] = 0.2
+                cps[node - 1, mesh.dofs[U.vmx] - 1] = 0.2
+        res = {}
+        for label, kw in (("host_buffers+scratch_lu", {}), ("resident+pattern_solver", {"resident": True, "solver": "pattern"})):
+            x, c = xms.copy(), cps.copy()
+            timers = {}
+            t0 = time.perf_counter()
+            hist = maf.run_analysis(mesh, x, c, p, timers=timers, **kw, **args)
+            wall = time.perf_counter() - t0
+            it = timers["iterations"]
+            res[label] = {"iterations": it, "assemble_call_ms": timers["assembly_s"] / it * 1e3,
+                          "host_solve_ms": timers["solve_s"] / it * 1e3, "newton_iteration_ms": wall / it * 1e3,
+                          "eps_first_step": hist[0]}
+        asm = maf.pkg.host.analysis._assembler(mesh, p, args)
+        # kernels alone, device-resident state: CUDA events around the launches of one assembly (maf_timings)
+        asm.state_set(xms, cps)
+        dev_ms, call_ms = [], []
+        r_buf, k_buf = np.empty(mesh.nmdf), np.empty(asm.nnz)
+        for _ in range(12):
+            t0 = time.perf_counter()
+            asm.assemble_resident(0.5, 0.5, r=r_buf, nzval=k_buf)
+            call_ms.append((time.perf_counter() - t0) * 1e3)
+            tm = asm.timings()
+            dev_ms.append(tm["zero_ms"] + tm["area_ms"] + tm["bdry_ms"])
+        res["kernels_device_ms"] = float(np.median(dev_ms[2:]))
+        res["assemble_resident_call_ms"] = float(np.median(call_ms[2:]))
+        res["nmdf"], res["nnz"], res["numel"] = int(mesh.nmdf), int(asm.nnz), int(mesh.numel)
+        maf.pkg.host.analysis.close_assemblers(mesh)
+        out[name] = res
+    return out
+
+
+def run_child(extra, timeout=900):
+    """Runs this script in a child process (keeps the oracle out of the timed process) and returns its JSON line."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR",
+                                                              "MASTER_PORT", "LOCAL_WORLD_SIZE", "GROUP_RANK")}
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + extra, capture_output=True, text=True,
+                           timeout=timeout, env=env, cwd=ROOT)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"error": (r.stderr or "no output")[-400:]}
+    except Exception as e:   # the bench line must still be printed
+        return {"error": repr(e)[:400]}
+
+
+def parity_spot(a):
+    """Child mode (--parity-spot): a few dozen single elements of the bench patch through the library against the
+    oracle's element routine and the extended-precision truth (tests/spot_parity.py; the GPU test suite runs > 300)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mafb200 as maf
+    from oracle import oracle as orc
+    from spot_parity import check_elements, select_elements
+    p = maf.Params(motion=getattr(maf, a.motion), scenario=maf.F_PULL, num1el=a.n, num2el=a.n, output=False)
+    mesh = maf.Mesh(p, pull_speed=0.5)
+    xms, cps = maf.synthetic_state(mesh, p)
+    kw = dict(motion=getattr(orc, a.motion), scenario=orc.F_PULL, num1el=a.n, num2el=a.n, length=p.length,
+              pull_speed=0.5)
+    om, ot = orc.Mesh(**kw), orc.Mesh(kind="truth", **kw)
+    asm = maf.Assembler(mesh, p, device=0)
+    dx = torch.from_numpy(np.ascontiguousarray(xms.T)).cuda()
+    dc = torch.from_numpy(np.ascontiguousarray(cps.T)).cuda()
+    els = select_elements(mesh, n_random=12)
+    els = els[::max(1, len(els) // 40)]
+    w = check_elements(asm, mesh, om, ot, dx.data_ptr(), dc.data_ptr(), xms, cps, 0.5, 0.5, els)
+    return {"elements_checked": w["n"], "what": "single elements via maf_set_element_range(el, el) vs the oracle's "
+            "elem_r_K scattered through LM and vs the extended-precision truth (tests/spot_parity.py)",
+            "dof_numbering_equal": bool(np.array_equal(om.ID, mesh.ID)),
+            "max_rel_diff_K_vs_oracle": w["K_rel_oracle"], "max_abs_diff_r_vs_oracle": w["r_abs_oracle"],
+            "strict_rule_worst_ratio": max(w["K_strict"], w["r_strict"]),
+            "gpu_error_in_eps_E": w["K_in_epsE"], "oracle_error_in_eps_E": w["oracle_in_epsE"],
+            "rule": "|x - truth| <= 1e-11 |truth| + eps E per entry (tests/cases.py), ratio <= 1 passes"}
 
 
 # ----------------------------------------------------------------------------------------------- main
@@ -171,12 +304,13 @@ def run(a, out_stream):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    import __graft_entry__ as ge
+    if a.parity_spot:
+        out_stream.write(json.dumps(parity_spot(a)) + "\n")
+        return 0
 
     if a.impl == "reference":
         if rank != 0:
             return 0
-        ge.build()
         cb, ms = cpu_reference_rate(a.motion, a.steps, a.warmup)
         out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -185,19 +319,21 @@ def run(a, out_stream):
                "cpu_baseline": cb,
                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
+        if a.newton_cpu:
+            out["newton_cpu"] = newton_cpu_times()
         out_stream.write(json.dumps(out) + "\n")
         return 0
 
     import torch
     import torch.distributed as dist
-    if rank == 0:
-        ge.build()
+    import mafb200 as maf
+    if rank == 0 and not os.path.exists(maf.pkg.capi.LIB_PATH):   # normally prebuilt (__graft_entry__.build)
+        subprocess.check_call([sys.executable, "-c", "import __graft_entry__ as g; g.build_cuda()"], cwd=ROOT)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
-    import mafb200 as maf
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
@@ -393,9 +529,21 @@ def run(a, out_stream):
                                  "balance ~5); the HBM fraction above is the schema's headline, this is the binding one"},
                 "other_kernels_ms": other}
 
-    cpu = None
+    # ---- everything that needs the oracle runs in child processes (this process maps libmembrane_b200.so only) ---
+    cpu, newton, spot = None, None, None
     if not a.no_cpu and world == 1:
-        cpu, _ = cpu_reference_rate(a.motion, 4, 1)
+        child = run_child(["--impl", "reference", "--steps", "4", "--warmup", "1", "--motion", a.motion] +
+                          ([] if a.no_newton else ["--newton-cpu"]))
+        cpu = child.get("cpu_baseline", child)
+        if not a.no_newton:
+            newton = newton_gpu_times(maf, local_rank)
+            for name, v in (child.get("newton_cpu") or {}).items():
+                newton.setdefault(name, {}).update(v)
+            newton["note"] = ("per Newton iteration on the reference's default 17x17 F_PULL mesh (configs 1-4; 4 = "
+                              "translate-ale emulation), 2 time steps: assembly call through the C ABI, host solve "
+                              "timed separately (SciPy SuperLU), CPU port of the reference assembly beside it")
+    if not a.no_spot and world == 1 and a.scatter == "atomic":
+        spot = run_child(["--parity-spot", "--motion", a.motion, "--patch-n", str(a.n)])
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -411,7 +559,7 @@ def run(a, out_stream):
                       if world > 1 else "single GPU",
                       "setup_s": t_setup, "kernel": asm.kernel_info()},
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-           "rnorm2": rnorm2}
+           "newton_iteration": newton, "parity_spot": spot, "rnorm2": rnorm2}
     out_stream.write(json.dumps(out) + "\n")
     if world > 1:
         dist.destroy_process_group()

@@ -523,6 +523,7 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const 
   const int mf = cfg.mesh_field;
   constexpr bool ALE = (MOTION == M_ALEV || MOTION == M_ALEVB);
 
+#ifndef MAF_STUB_GEO_A
   if (it.type == IT_GEO_A) {
     Dual ad[2][3];
 #pragma unroll
@@ -550,6 +551,7 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const 
     store_column(cfg, Agp, w, S, mf, it.j, CH_N1 + it.gamma);
     return;
   }
+#endif
 
   GpGeom<double> g;
   gp_geom(a, g);
@@ -561,6 +563,7 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const 
     for (int mu = 0; mu < 2; ++mu) Gam[k][mu] = c[k][0] * g.up[mu][0] + c[k][1] * g.up[mu][1] + c[k][2] * g.up[mu][2];
   }
 
+#ifndef MAF_STUB_GEO_B
   if (it.type == IT_GEO_B) {
     // one item per b-direction k (it.gamma): the three directions of a Gauss point run on three lanes
     const double wdt = w * dt;
@@ -597,6 +600,7 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const 
     }
     return;
   }
+#endif
 
   // ---- IT_LIN: primal stresses -> S[gp] ----
   GpStress<double> S;

@@ -33,8 +33,22 @@ def _assembler(mesh, p, args):
 
 def close_assemblers(mesh):
     """Release every cached handle of this mesh (each holds the device copies of the tables, r and nzval)."""
+    for sol in mesh.__dict__.pop("_solvers", {}).values():
+        sol.close()
     for asm in mesh.__dict__.pop("_assemblers", {}).values():
         asm.close()
+
+
+def _pattern_solver(mesh, p, args):
+    """The host solver that owns the value buffer of K on the fixed pattern (host/solver.py)."""
+    from ..capi import host_register, host_unregister
+    from .solver import PatternSolver
+    key = (p, args.get("pattern_mode", PATTERN_BLK), args.get("device", -1))
+    cache = mesh.__dict__.setdefault("_solvers", {})
+    if key not in cache:
+        colptr, rowval = _assembler(mesh, p, args).pattern()
+        cache[key] = PatternSolver(colptr, rowval, mesh.nmdf, register=host_register, unregister=host_unregister)
+    return cache[key]
 
 
 def calc_r_K(mesh, xms, cps, time, dt, p, **args):
@@ -68,29 +82,38 @@ def time_step(mesh, xms, cps, time, dt, p, **args):
 
     Returns the list of ε = ‖Δu‖₂ / nmdf per iteration (the reference prints it, :50). The sparse solve stays on
     the host (SciPy SuperLU stands in for Julia's UMFPACK `\\`); its time is accumulated in args['timers'].
+    solver="pattern" selects the hand-off of host/solver.py: maf_assemble writes nzval into the page-locked buffer
+    the solver owns, and the column ordering is chosen once per pattern instead of once per iteration.
     """
     eps_hist = []
     timers = args.get("timers")
     log = args.get("log")
     node_of, dof_of = mesh.ID_inv
     resident = bool(args.get("resident", False))
-    if resident:   # the state lives on the device for the whole step; only r / K come back and du goes in
+    solver = _pattern_solver(mesh, p, args) if args.get("solver") == "pattern" else None
+    if resident or solver is not None:
         asm = _assembler(mesh, p, args)
-        asm.state_set(xms, cps)
         colptr, rowval = asm.pattern()
+    if resident:   # the state lives on the device for the whole step; only r / K come back and du goes in
+        asm.state_set(xms, cps)
     it = 1
     while it < 15:
         t0 = _time.perf_counter()
+        kw = dict(bend_tm=float(args.get("bend_tm", 1.0)), scatter_mode=args.get("scatter_mode", SCATTER_ATOMIC))
+        if solver is not None:     # f2 hand-off: the values land in the buffer the solver factorises
+            kw["nzval"] = solver.nzval
         if resident:
-            r_gl, nzval, _ = asm.assemble_resident(float(time), float(dt), bend_tm=float(args.get("bend_tm", 1.0)),
-                                                   scatter_mode=args.get("scatter_mode", SCATTER_ATOMIC))
+            r_gl, nzval, _ = asm.assemble_resident(float(time), float(dt), **kw)
+        elif solver is not None:
+            r_gl, nzval, _ = asm.assemble(xms, cps, float(time), float(dt), **kw)
+        if solver is None and resident:
             K_gl = sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(mesh.nmdf, mesh.nmdf))
             if args.get("dropzeros", True):
                 K_gl.eliminate_zeros()
-        else:
+        elif solver is None:
             r_gl, K_gl = calc_r_K(mesh, xms, cps, time, dt, p, **args)
         t1 = _time.perf_counter()
-        du = -spla.splu(K_gl.tocsc()).solve(r_gl)
+        du = -(solver.solve(r_gl) if solver is not None else spla.splu(K_gl.tocsc()).solve(r_gl))
         t2 = _time.perf_counter()
         if resident:
             asm.state_update(du, float(dt))
