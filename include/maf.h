@@ -155,7 +155,8 @@ int maf_kernel_info(maf_handle* h, int64_t* out5);
  * counterpart: the reference's element loop (FiniteElement.jl:98-140) is scheduled by Julia's task runtime. */
 int maf_chunk_plan(maf_handle* h, char* text, int64_t cap);
 
-/* Multi-GPU (one process per GPU, every process holds the same mesh tables): restrict this handle to the elements
+/* Element ranges on a whole-mesh handle (spot checks, and the round-1 multi-GPU path where every process holds all
+ * tables and buffers; the strip handles above supersede it): restrict this handle to the elements
  * [el_first, el_last] (1-based, inclusive) -- contiguous element ids are strips of element rows (Mesh.jl:582-588).
  * Because unknowns are numbered node-major (Mesh.jl:276-284) a strip touches one contiguous range of rows of r and
  * one contiguous range of nzval; maf_range_info returns them (all 1-based, inclusive):
@@ -165,6 +166,48 @@ int maf_chunk_plan(maf_handle* h, char* text, int64_t cap);
  * collective (NCCL send/recv between neighbours) -- nothing else crosses GPUs. */
 int maf_set_element_range(maf_handle* h, int64_t el_first, int64_t el_last);
 int maf_range_info(maf_handle* h, int64_t* out8);
+
+/* ---- Strips over several GPUs behind the boundary --------------------------------------------------
+ * The reference splits the element loop into contiguous chunks, one per Julia task with private r / K, and sums them
+ * (FiniteElement.jl:88-89, 144-147). Here a chunk is a strip of element rows on its own GPU; one handle per strip,
+ * driven by one host thread for all GPUs of a process or by one process per GPU:
+ *
+ *   maf_create_strip(out, mesh, params, rank, nranks)
+ *        like maf_create, for strip `rank` (element rows [rank num2el / nranks, (rank + 1) num2el / nranks), at least
+ *        two rows per strip). Allocates only what the strip needs: the scatter maps of its own elements and the
+ *        slices of r / nzval its elements touch (memory per GPU ~ 1 / nranks; the node-major numbering of
+ *        Mesh.jl:276-284 makes both slices contiguous). params->device selects the GPU.
+ *   maf_strip_info(h, out12)   1-based inclusive: out[0..1] elements, [2..3] rows of r touched, [4..5] entries of
+ *        nzval touched, [6..7] rows OWNED, [8..9] entries OWNED, [10] rank, [11] nranks. Neighbouring strips overlap
+ *        in the two node rows they share; those belong to the UPPER strip, so the owned ranges tile 1..nmdf / 1..nnz.
+ *   maf_peer_attach_local(h, lower, upper)       same process: the handles of the strips rank-1 / rank+1 (NULL at
+ *        the ends); enables peer access between their devices.
+ *   maf_peer_export(h, handle64) / maf_peer_attach(h, lower64, upper64)   one process per GPU: 64-byte export
+ *        (a cudaIpcMemHandle_t) of a strip's result buffer, exchanged by the caller (any transport), NULL at the ends.
+ *   maf_assemble_strip(h, d_xms, d_cps, time, dt, bend_tm, mode, d_rnorm2_partial)
+ *        the strip's share of calc_r_K, asynchronous on the handle's stream: its elements are assembled into its
+ *        slices, then the upper strip of every pair ADDS the lower strip's partial sums of the interface, reading them
+ *        straight from the neighbour's memory over NVLink (peer loads; two flags per pair order it -- no NCCL
+ *        payload, no host round trip). d_xms / d_cps: device pointers of the full state arrays, or NULL for the
+ *        handle's resident state. d_rnorm2_partial (device, may be NULL = the handle's own word): sum(r^2) over the
+ *        OWNED rows -- the caller adds the partials of all strips (one scalar all-reduce).
+ *   maf_assemble_strip_host(...)   same with host buffers: uploads only the node rows the strip reads, assembles,
+ *        copies the OWNED rows / entries into r_own / nzval_own (sizes from maf_strip_info). Blocking.
+ *   maf_strip_timings(h, out2)  out[0] ms between the end of the strip's kernels and the end of the interface
+ *        exchange of the last assembly, out[1] bytes of the strip's result allocation.
+ * All strips must run the same sequence of assemblies (the flags count them); a neighbour that does not arrive within
+ * ~10 s is reported as an error by the next blocking call instead of hanging the device. */
+int maf_create_strip(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* params, int32_t rank,
+                     int32_t nranks);
+int maf_strip_info(maf_handle* h, int64_t* out12);
+int maf_peer_attach_local(maf_handle* h, maf_handle* lower, maf_handle* upper);
+int maf_peer_export(maf_handle* h, void* handle64);
+int maf_peer_attach(maf_handle* h, const void* lower64, const void* upper64);
+int maf_assemble_strip(maf_handle* h, const double* d_xms, const double* d_cps, double time, double dt, double bend_tm,
+                       int scatter_mode, double* d_rnorm2_partial);
+int maf_assemble_strip_host(maf_handle* h, const double* xms, const double* cps, double time, double dt, double bend_tm,
+                            int scatter_mode, double* r_own, double* nzval_own, double* rnorm2_partial);
+int maf_strip_timings(maf_handle* h, double* out2);
 
 /* ---- Device-resident state: the glue of time_step! between two calls of calc_r_K ----------------
  * With these the state never returns to the host inside a time step; per Newton iteration only r / nzval come back

@@ -46,7 +46,9 @@ EXPORTS = ["maf_create", "maf_destroy", "maf_last_error", "maf_nnz", "maf_patter
            "maf_kernel_info", "maf_chunk_plan", "maf_set_element_range", "maf_range_info", "maf_fp64_peak",
            "maf_debug_phase_cycles", "maf_state_set", "maf_state_get", "maf_state_update", "maf_state_predict",
            "maf_assemble_resident", "maf_elem_v_residuals", "maf_host_register", "maf_host_unregister",
-           "maf_colptr", "maf_pattern_columns", "maf_download"]
+           "maf_colptr", "maf_pattern_columns", "maf_download", "maf_create_strip", "maf_strip_info",
+           "maf_peer_attach_local", "maf_peer_export", "maf_peer_attach", "maf_assemble_strip",
+           "maf_assemble_strip_host", "maf_strip_timings"]
 
 
 def load_library(path=None):
@@ -65,6 +67,16 @@ def load_library(path=None):
     L.maf_destroy.argtypes = [C.c_void_p]
     L.maf_nnz.argtypes = [C.c_void_p, _I64P]
     L.maf_pattern.argtypes = [C.c_void_p, _I64P, _I64P]
+    L.maf_create_strip.argtypes = [C.POINTER(C.c_void_p), C.POINTER(MeshDesc), C.POINTER(ParamsC), C.c_int32, C.c_int32]
+    L.maf_strip_info.argtypes = [C.c_void_p, _I64P]
+    L.maf_peer_attach_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.maf_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.maf_peer_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.maf_assemble_strip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int,
+                                     C.c_void_p]
+    L.maf_assemble_strip_host.argtypes = [C.c_void_p, _F64P, _F64P, C.c_double, C.c_double, C.c_double, C.c_int,
+                                          _F64P, _F64P, _F64P]
+    L.maf_strip_timings.argtypes = [C.c_void_p, _F64P]
     L.maf_colptr.argtypes = [C.c_void_p, _I64P]
     L.maf_pattern_columns.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _I64P]
     L.maf_download.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _F64P, C.c_int64, C.c_int64, _F64P]
@@ -154,14 +166,20 @@ def host_unregister(arr, lib=None):
 class Assembler:
     """Owner of one maf_handle: the device-resident replacement of the reference's calc_r_K for one (mesh, Params)."""
 
-    def __init__(self, mesh, p, pattern_mode=PATTERN_BLK, device=-1, lib=None):
+    def __init__(self, mesh, p, pattern_mode=PATTERN_BLK, device=-1, lib=None, strip=None):
+        """strip = (rank, nranks): a strip handle (maf_create_strip) that holds only the slices of one strip of element
+        rows; None: the whole mesh on one device (maf_create)."""
         self.L = lib or load_library()
         self.mesh, self.p = mesh, p
         keep = []
         desc = make_mesh_desc(mesh, keep)
         par = ParamsC(int(p.motion), int(p.scenario), p.kb, p.kg, p.zv, p.pn, p.adb, p.am, pattern_mode, device)
         h = C.c_void_p()
-        rc = self.L.maf_create(C.byref(h), C.byref(desc), C.byref(par))
+        self.strip = strip
+        if strip is None:
+            rc = self.L.maf_create(C.byref(h), C.byref(desc), C.byref(par))
+        else:
+            rc = self.L.maf_create_strip(C.byref(h), C.byref(desc), C.byref(par), int(strip[0]), int(strip[1]))
         if rc != 0:
             raise MafError(f"maf_create failed ({rc}): {self.L.maf_last_error(None).decode()}")
         self.h = h
@@ -304,6 +322,51 @@ class Assembler:
         buf = C.create_string_buffer(1024)
         self._check(self.L.maf_chunk_plan(self.h, buf, 1024))
         return buf.value.decode()
+
+    # ---- strips over several GPUs (include/maf.h: maf_create_strip ...) ----
+    def strip_info(self):
+        o = np.zeros(12, dtype=np.int64)
+        self._check(self.L.maf_strip_info(self.h, _ptr(o, C.c_int64)))
+        return {"elements": (int(o[0]), int(o[1])), "rows": (int(o[2]), int(o[3])), "slots": (int(o[4]), int(o[5])),
+                "own_rows": (int(o[6]), int(o[7])), "own_slots": (int(o[8]), int(o[9])), "rank": int(o[10]),
+                "nranks": int(o[11])}
+
+    def peer_attach_local(self, lower, upper):
+        self._check(self.L.maf_peer_attach_local(self.h, lower.h if lower is not None else None,
+                                                 upper.h if upper is not None else None))
+
+    def peer_export(self):
+        buf = (C.c_ubyte * 64)()
+        self._check(self.L.maf_peer_export(self.h, buf))
+        return bytes(buf)
+
+    def peer_attach(self, lower64, upper64):
+        lo = (C.c_ubyte * 64).from_buffer_copy(lower64) if lower64 is not None else None
+        up = (C.c_ubyte * 64).from_buffer_copy(upper64) if upper64 is not None else None
+        self._check(self.L.maf_peer_attach(self.h, lo, up))
+
+    def assemble_strip(self, d_xms, d_cps, time, dt, bend_tm=1.0, scatter_mode=SCATTER_ATOMIC, d_rnorm2_partial=None):
+        self._check(self.L.maf_assemble_strip(self.h, d_xms, d_cps, time, dt, bend_tm, scatter_mode, d_rnorm2_partial))
+
+    def assemble_strip_host(self, xms, cps, time, dt, bend_tm=1.0, scatter_mode=SCATTER_ATOMIC, r_own=None,
+                            nzval_own=None):
+        """maf_assemble_strip_host: returns (r_own, nzval_own, partial sum(r^2) over the owned rows)."""
+        info = self.strip_info()
+        nr = info["own_rows"][1] - info["own_rows"][0] + 1
+        nk = info["own_slots"][1] - info["own_slots"][0] + 1
+        r_own = np.empty(nr) if r_own is None else r_own
+        nzval_own = np.empty(nk) if nzval_own is None else nzval_own
+        rn = C.c_double()
+        xp = _ptr(np.asfortranarray(xms, dtype=np.float64), C.c_double) if xms is not None else None
+        cp = _ptr(np.asfortranarray(cps, dtype=np.float64), C.c_double) if cps is not None else None
+        self._check(self.L.maf_assemble_strip_host(self.h, xp, cp, time, dt, bend_tm, scatter_mode,
+                                                   _ptr(r_own, C.c_double), _ptr(nzval_own, C.c_double), C.byref(rn)))
+        return r_own, nzval_own, rn.value
+
+    def strip_timings(self):
+        o = np.zeros(2)
+        self._check(self.L.maf_strip_timings(self.h, _ptr(o, C.c_double)))
+        return {"exchange_ms": float(o[0]), "result_bytes": int(o[1])}
 
     def set_element_range(self, el_first, el_last):
         self._check(self.L.maf_set_element_range(self.h, el_first, el_last))

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128)
 build_elslot_kernel(const Tables T, int32_t* __restrict__ elslot, int64_t* __restrict__ elbase, int* __restrict__ overflow) {
   __shared__ long long s_col[72];
   __shared__ long long s_base;
-  const int64_t el = blockIdx.x;
+  const int64_t el = T.el0 + blockIdx.x;   // (a strip handle builds the maps of its own elements only)
   const int tid = threadIdx.x;
   if (tid < 72) s_col[tid] = T.nodecol[8 * (int64_t)T.IX[9 * el + (tid >> 3)] + (tid & 7)];
   __syncthreads();
@@ -168,7 +168,7 @@ build_elslot_kernel(const Tables T, int32_t* __restrict__ elslot, int64_t* __res
     for (int k = 0; k < 72; ++k)
       if (s_col[k] >= 0 && (base < 0 || s_col[k] < base)) base = s_col[k];
     s_base = base < 0 ? 0 : base;
-    elbase[el] = s_base;
+    elbase[el - T.el0] = s_base;
   }
   __syncthreads();
   const long long base = s_base;
@@ -179,13 +179,13 @@ build_elslot_kernel(const Tables T, int32_t* __restrict__ elslot, int64_t* __res
       if (J < 8) {
         const long long c = s_col[8 * b + J];
         if (c >= 0) {
-          const long long off = c - base + T.pairoff[(int64_t)T.elpair[81 * el + 9 * a + b] * 8 + J];
+          const long long off = c - base + T.pairoff[(int64_t)T.elpair[81 * (el - T.el0) + 9 * a + b] * 8 + J];
           if (off > 0x7fffff00LL) *overflow = 1;
           v = (int32_t)off;
         }
       }
     }
-    elslot[(size_t)MAF_SLOT_INTS * el + k] = v;
+    elslot[(size_t)MAF_SLOT_INTS * (el - T.el0) + k] = v;
   }
 }
 
@@ -305,6 +305,33 @@ __global__ void rnorm2_final(const double* part, int n, double* out) {
   if (threadIdx.x == 0) *out = s[0];
 }
 
+// ---- strips over several GPUs: the "sum over tasks" of FiniteElement.jl:144-147 for the two node rows neighbouring
+// strips share. No NCCL payload: the strip that owns the interface (the upper one) reads the lower strip's partial
+// sums straight out of its memory over NVLink (peer loads) and adds them; two flags per neighbour pair order it.
+//   flag_kernel   one thread: publish `sval` at *signal (a word in the NEIGHBOUR's memory) after a system-scope fence,
+//                 then spin until *wait (a word in OUR memory, written by the neighbour) reaches `wval`
+//   pull_add      dst[i] += src[i], src = mapped peer memory
+__global__ void flag_kernel(volatile long long* signal, long long sval, volatile long long* wait, long long wval,
+                            long long* err, long long max_spins) {
+  if (signal) {
+    __threadfence_system();
+    *signal = sval;
+    __threadfence_system();
+  }
+  if (wait) {
+    long long n = 0;
+    while (*wait < wval) {
+      if (++n > max_spins) { *err = wval; break; }   // a neighbour that never arrives must not hang the device
+      __nanosleep(200);
+    }
+    __threadfence_system();
+  }
+}
+__global__ void __launch_bounds__(256) pull_add_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t n) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    dst[k] += __ldcv(src + k);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------------------------------------
@@ -341,7 +368,29 @@ struct maf_handle {
   std::vector<cudaEvent_t> strip_ev;
   int64_t launches = 0;
   float ms[7] = {0, 0, 0, 0, 0, 0, 0};
+  // ---- strip mode (maf_create_strip): this handle holds the slices of ONE strip of element rows
+  bool strip = false;
+  int rank = 0, nranks = 1;
+  TouchedRange lower, upper;          // what the neighbouring strips touch (empty ranges at the ends)
+  int64_t own_eq_lo = 0, own_eq_hi = 0, own_slot_lo = 0, own_slot_hi = 0;   // rows / entries this strip hands out
+  void* strip_alloc = nullptr;        // one allocation: flags | r slice | nzval slice (one IPC handle exports it)
+  size_t strip_bytes = 0;
+  long long* flags = nullptr;         // [0] lower finished step, [1] upper has pulled step, [2] error (our memory)
+  void* lower_base = nullptr;         // the neighbours' allocations, mapped (IPC or same-process peer access)
+  void* upper_base = nullptr;
+  bool lower_ipc = false, upper_ipc = false, attached = false;
+  long long step = 0;                 // assemblies done (the flags carry it)
+  cudaEvent_t ev_x[4] = {};
+  float ms_exchange = 0.f;
 };
+// layout of a strip allocation: 256 bytes of flags, the r slice, the nzval slice (each padded to 256 bytes)
+static size_t strip_r_offset() { return 256; }
+static size_t strip_nz_offset(const TouchedRange& R) {
+  return 256 + (((size_t)(R.eq_hi - R.eq_lo) * sizeof(double) + 255) / 256) * 256;
+}
+static size_t strip_alloc_bytes(const TouchedRange& R) {
+  return strip_nz_offset(R) + (((size_t)(R.slot_hi - R.slot_lo) * sizeof(double) + 255) / 256) * 256 + 256;
+}
 
 static std::string g_create_err;
 static std::mutex g_mu;
@@ -396,22 +445,10 @@ static elres_fn elem_residual_kernel_of(int motion) {
 // what the element range [e0, e1) touches: node, equation and nnz-slot ranges (each contiguous)
 static void compute_ranges(maf_handle* h) {
   const HostModel& M = h->M;
-  int64_t lo = M.numnp, hi = -1;
-  for (int64_t k = 9 * h->e0; k < 9 * h->e1; ++k) {
-    lo = std::min<int64_t>(lo, M.IX0[k]);
-    hi = std::max<int64_t>(hi, M.IX0[k]);
-  }
-  if (hi < 0) { lo = 0; hi = -1; }
-  h->node_lo = lo;
-  h->node_hi = hi + 1;
-  int64_t eq_lo = M.nmdf, eq_hi = 0;
-  for (int64_t k = lo * M.ndf; k < (hi + 1) * M.ndf; ++k)
-    if (M.ID0[k] >= 0) { eq_lo = std::min<int64_t>(eq_lo, M.ID0[k]); eq_hi = std::max<int64_t>(eq_hi, M.ID0[k] + 1); }
-  if (eq_hi <= eq_lo) eq_lo = eq_hi = 0;
-  h->eq_lo = eq_lo;
-  h->eq_hi = eq_hi;
-  h->slot_lo = M.sym.colptr[eq_lo];
-  h->slot_hi = M.sym.colptr[eq_hi];
+  const TouchedRange R = touched_range(M, h->e0, h->e1);
+  h->node_lo = R.node_lo; h->node_hi = R.node_hi;
+  h->eq_lo = R.eq_lo; h->eq_hi = R.eq_hi;
+  h->slot_lo = R.slot_lo; h->slot_hi = R.slot_hi;
   std::vector<int32_t> order;
   build_element_order(M.num1el, h->e0, h->e1, order);
   if (h->d_order) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFree(h->d_order)); h->d_order = nullptr; }
@@ -601,6 +638,8 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
 
 extern "C" {
 
+static void upload_state_rows(maf_handle* h, const double* xms, const double* cps);
+
 const char* maf_last_error(const maf_handle* h) {
   if (h) return h->err.c_str();
   std::lock_guard<std::mutex> lk(g_mu);
@@ -609,7 +648,8 @@ const char* maf_last_error(const maf_handle* h) {
   return copy.c_str();
 }
 
-int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* params) {
+// rank < 0: the whole mesh on one device (maf_create); otherwise strip `rank` of `nranks` (maf_create_strip)
+static int create_handle(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* params, int rank, int nranks) {
   if (!out) return 1;
   *out = nullptr;
   maf_handle* h = new (std::nothrow) maf_handle();
@@ -633,6 +673,23 @@ int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* pa
     HostModel& M = h->M;
     h->e0 = 0;
     h->e1 = M.numel;
+    if (rank >= 0) {
+      h->strip = true;
+      h->rank = rank;
+      h->nranks = nranks;
+      const TouchedRange R = strip_range(M, rank, nranks);
+      h->e0 = R.e0;
+      h->e1 = R.e1;
+      if (rank > 0) h->lower = strip_range(M, rank - 1, nranks);
+      if (rank + 1 < nranks) h->upper = strip_range(M, rank + 1, nranks);
+      // the interface (the node rows two strips share) belongs to the UPPER strip: a strip hands out what it touches
+      // below the first row / slot of the next strip
+      h->own_eq_lo = R.eq_lo; h->own_slot_lo = R.slot_lo;
+      h->own_eq_hi = rank + 1 < nranks ? h->upper.eq_lo : R.eq_hi;
+      h->own_slot_hi = rank + 1 < nranks ? h->upper.slot_lo : R.slot_hi;
+      if (rank > 0 && (h->lower.eq_hi > R.eq_hi || h->lower.slot_hi > R.slot_hi || h->lower.eq_lo > R.eq_lo))
+        throw std::runtime_error("internal: strip ranges are not nested as expected");
+    }
     compute_ranges(h);
 
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -647,7 +704,10 @@ int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* pa
     h->T.line2 = upload(h, M.line2.data(), M.line2.size());
     h->T.tdb = upload(h, M.tdb.data(), M.tdb.size());
     h->T.colptr = upload(h, M.sym.colptr.data(), M.sym.colptr.size());
-    h->T.elpair = upload(h, M.sym.elpair.data(), M.sym.elpair.size());
+    // per-element tables: a strip keeps its own elements only (memory per rank ~ 1 / nranks)
+    h->T.el0 = h->strip ? h->e0 : 0;
+    const int64_t nel_tab = h->strip ? h->e1 - h->e0 : M.numel;
+    h->T.elpair = upload(h, M.sym.elpair.data() + (size_t)81 * h->T.el0, (size_t)81 * nel_tab);
     h->T.pairoff = upload(h, M.sym.pairoff.data(), M.sym.pairoff.size());
     h->T.eq0 = upload(h, M.sym.eq0.data(), M.sym.eq0.size());
     h->T.nodecol = upload(h, M.nodecol.data(), M.nodecol.size());
@@ -655,11 +715,11 @@ int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* pa
     h->T.utab = M.utab.empty() ? nullptr : upload(h, M.utab.data(), M.utab.size());
     h->T.numnp = M.numnp; h->T.numel = M.numel; h->T.num1el = M.num1el; h->T.nuel1 = M.nuel1;
     {   // per-element scatter maps, built on the device from the tables above (2.9 KB per element)
-      int32_t* d_slot = dalloc<int32_t>(h, (size_t)MAF_SLOT_INTS * M.numel);
-      int64_t* d_base = dalloc<int64_t>(h, (size_t)M.numel);
+      int32_t* d_slot = dalloc<int32_t>(h, (size_t)MAF_SLOT_INTS * nel_tab);
+      int64_t* d_base = dalloc<int64_t>(h, (size_t)nel_tab);
       int* d_ovf = dalloc<int>(h, 1);
       CU(cudaMemsetAsync(d_ovf, 0, sizeof(int), h->stream));
-      if (M.numel > 0) build_elslot_kernel<<<(unsigned)M.numel, 128, 0, h->stream>>>(h->T, d_slot, d_base, d_ovf);
+      if (nel_tab > 0) build_elslot_kernel<<<(unsigned)nel_tab, 128, 0, h->stream>>>(h->T, d_slot, d_base, d_ovf);
       CU(cudaGetLastError());
       int ovf = 0;
       CU(cudaMemcpyAsync(&ovf, d_ovf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -680,8 +740,23 @@ int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* pa
     // uploaded on first use (ensure_gather)
     h->d_xms = dalloc<double>(h, (size_t)3 * M.numnp);
     h->d_cps = dalloc<double>(h, (size_t)M.ndf * M.numnp);
-    h->d_r = dalloc<double>(h, (size_t)M.nmdf);
-    h->d_nz = dalloc<double>(h, (size_t)M.sym.nnz);
+    if (!h->strip) {
+      h->d_r = dalloc<double>(h, (size_t)M.nmdf);
+      h->d_nz = dalloc<double>(h, (size_t)M.sym.nnz);
+    } else {
+      // ONE allocation (exported to the neighbours as one IPC handle): flags | r slice | nzval slice. d_r / d_nz are
+      // kept as VIRTUAL bases (slice start minus the first row / slot of the slice) so that every kernel keeps
+      // addressing rows and slots by their global index; only [eq_lo, eq_hi) / [slot_lo, slot_hi) is ever touched.
+      TouchedRange R;
+      R.eq_lo = h->eq_lo; R.eq_hi = h->eq_hi; R.slot_lo = h->slot_lo; R.slot_hi = h->slot_hi;
+      h->strip_bytes = strip_alloc_bytes(R);
+      CU(cudaMalloc(&h->strip_alloc, h->strip_bytes));
+      CU(cudaMemset(h->strip_alloc, 0, h->strip_bytes));
+      h->flags = reinterpret_cast<long long*>(h->strip_alloc);
+      h->d_r = reinterpret_cast<double*>((char*)h->strip_alloc + strip_r_offset()) - h->eq_lo;
+      h->d_nz = reinterpret_cast<double*>((char*)h->strip_alloc + strip_nz_offset(R)) - h->slot_lo;
+      for (int k = 0; k < 4; ++k) CU(cudaEventCreate(&h->ev_x[k]));
+    }
     h->d_rn = dalloc<double>(h, 1);
     h->d_part = dalloc<double>(h, 256);
     std::vector<int32_t>().swap(M.sym.elpair);
@@ -712,10 +787,30 @@ int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* pa
   return 0;
 }
 
+int maf_create(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* params) {
+  return create_handle(out, mesh, params, -1, 1);
+}
+
+int maf_create_strip(maf_handle** out, const maf_mesh_desc* mesh, const maf_params* params, int32_t rank,
+                     int32_t nranks) {
+  if (rank < 0 || nranks < 1 || rank >= nranks) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_create_err = "strip rank outside 0..nranks-1";
+    if (out) *out = nullptr;
+    return 2;
+  }
+  return create_handle(out, mesh, params, rank, nranks);
+}
+
 int maf_destroy(maf_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->lower_base && h->lower_ipc) cudaIpcCloseMemHandle(h->lower_base);
+  if (h->upper_base && h->upper_ipc) cudaIpcCloseMemHandle(h->upper_base);
+  if (h->strip_alloc) cudaFree(h->strip_alloc);
+  for (int k = 0; k < 4; ++k)
+    if (h->ev_x[k]) cudaEventDestroy(h->ev_x[k]);
   for (void* p : h->allocs) cudaFree(p);
   if (h->d_order) cudaFree(h->d_order);
   for (auto& st : h->strips) cudaFree(st.d_order);
@@ -870,6 +965,7 @@ static void assemble_to_host(maf_handle* h, double time, double dt, double bend_
 int maf_assemble(maf_handle* h, const double* xms, const double* cps, double time, double dt, double bend_tm,
                  int scatter_mode, double* r, double* nzval, double* rnorm2) {
   MAF_API_BEGIN(h)
+  if (h->strip) throw std::runtime_error("strip handle: use maf_assemble_strip / maf_assemble_strip_host");
   if (!xms || !cps || !r || !nzval) throw std::runtime_error("null buffer");
   CU(cudaEventRecord(h->ev[0], h->stream));
   upload_state(h, xms, cps);
@@ -885,6 +981,11 @@ static void require_state(maf_handle* h) {
 int maf_state_set(maf_handle* h, const double* xms, const double* cps) {
   MAF_API_BEGIN(h)
   if (!xms || !cps) throw std::runtime_error("null buffer");
+  if (h->strip) {   // only the node rows the strip reads (the arrays are the caller's full ones)
+    upload_state_rows(h, xms, cps);
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
   upload_state(h, xms, cps);
   CU(cudaStreamSynchronize(h->stream));   // the caller may reuse its buffers
   MAF_API_END(h)
@@ -932,6 +1033,7 @@ int maf_assemble_resident(maf_handle* h, double time, double dt, double bend_tm,
                           double* nzval, double* rnorm2) {
   MAF_API_BEGIN(h)
   require_state(h);
+  if (h->strip) throw std::runtime_error("strip handle: use maf_assemble_strip / maf_assemble_strip_host");
   CU(cudaEventRecord(h->ev[0], h->stream));
   assemble_to_host(h, time, dt, bend_tm, scatter_mode, r, nzval, rnorm2);
   MAF_API_END(h)
@@ -984,6 +1086,8 @@ int maf_assemble_device(maf_handle* h, const double* d_xms, const double* d_cps,
                         void* stream) {
   MAF_API_BEGIN(h)
   if (!d_xms || !d_cps) throw std::runtime_error("null device buffer");
+  if (h->strip && (d_r || d_nzval || d_rnorm2))
+    throw std::runtime_error("strip handle: results go to the handle's own slices (maf_assemble_strip)");
   do_assemble_device(h, d_xms, d_cps, time, dt, bend_tm, scatter_mode, d_r, d_nzval, d_rnorm2,
                      stream ? (cudaStream_t)stream : h->stream, false);
   MAF_API_END(h)
@@ -1008,6 +1112,9 @@ int maf_download(maf_handle* h, int64_t r_first, int64_t r_count, double* r, int
   if (r_count > 0 && (!r || r_first < 1 || r_first + r_count - 1 > M.nmdf)) throw std::runtime_error("row range outside 1..nmdf");
   if (nz_count > 0 && (!nzval || nz_first < 1 || nz_first + nz_count - 1 > M.sym.nnz))
     throw std::runtime_error("entry range outside 1..nnz");
+  if (h->strip && ((r_count > 0 && (r_first - 1 < h->eq_lo || r_first - 1 + r_count > h->eq_hi)) ||
+                   (nz_count > 0 && (nz_first - 1 < h->slot_lo || nz_first - 1 + nz_count > h->slot_hi))))
+    throw std::runtime_error("a strip handle holds only the rows / entries its elements touch (maf_strip_info)");
   if (r_count > 0)
     CU(cudaMemcpyAsync(r, h->d_r + (r_first - 1), sizeof(double) * (size_t)r_count, cudaMemcpyDeviceToHost, h->stream));
   if (nz_count > 0)
@@ -1080,8 +1187,196 @@ int maf_chunk_plan(maf_handle* h, char* text, int64_t cap) {
   MAF_API_END(h)
 }
 
+// ---- strips over several GPUs ------------------------------------------------------------------------------------
+static void require_strip(maf_handle* h) {
+  if (!h->strip) throw std::runtime_error("not a strip handle: create it with maf_create_strip");
+}
+
+int maf_strip_info(maf_handle* h, int64_t* out12) {
+  MAF_API_BEGIN(h)
+  require_strip(h);
+  if (!out12) throw std::runtime_error("null output pointer");
+  out12[0] = h->e0 + 1; out12[1] = h->e1;
+  out12[2] = h->eq_lo + 1; out12[3] = h->eq_hi;
+  out12[4] = h->slot_lo + 1; out12[5] = h->slot_hi;
+  out12[6] = h->own_eq_lo + 1; out12[7] = h->own_eq_hi;
+  out12[8] = h->own_slot_lo + 1; out12[9] = h->own_slot_hi;
+  out12[10] = h->rank; out12[11] = h->nranks;
+  MAF_API_END(h)
+}
+
+int maf_peer_export(maf_handle* h, void* handle64) {
+  MAF_API_BEGIN(h)
+  require_strip(h);
+  if (!handle64) throw std::runtime_error("null output pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t ipc;
+  CU(cudaIpcGetMemHandle(&ipc, h->strip_alloc));
+  std::memcpy(handle64, &ipc, 64);
+  MAF_API_END(h)
+}
+
+int maf_peer_attach(maf_handle* h, const void* lower64, const void* upper64) {
+  MAF_API_BEGIN(h)
+  require_strip(h);
+  if (h->attached) throw std::runtime_error("neighbours are already attached");
+  if ((h->rank > 0) != (lower64 != nullptr) || (h->rank + 1 < h->nranks) != (upper64 != nullptr))
+    throw std::runtime_error("pass the export of exactly the neighbouring strips that exist (NULL at the ends)");
+  cudaIpcMemHandle_t ipc;
+  if (lower64) {
+    std::memcpy(&ipc, lower64, 64);
+    CU(cudaIpcOpenMemHandle(&h->lower_base, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->lower_ipc = true;
+  }
+  if (upper64) {
+    std::memcpy(&ipc, upper64, 64);
+    CU(cudaIpcOpenMemHandle(&h->upper_base, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->upper_ipc = true;
+  }
+  h->attached = true;
+  MAF_API_END(h)
+}
+
+int maf_peer_attach_local(maf_handle* h, maf_handle* lower, maf_handle* upper) {
+  MAF_API_BEGIN(h)
+  require_strip(h);
+  if (h->attached) throw std::runtime_error("neighbours are already attached");
+  if ((h->rank > 0) != (lower != nullptr) || (h->rank + 1 < h->nranks) != (upper != nullptr))
+    throw std::runtime_error("pass exactly the neighbouring strip handles that exist (NULL at the ends)");
+  for (maf_handle* nb : {lower, upper}) {
+    if (!nb) continue;
+    if (!nb->strip || nb->nranks != h->nranks || (nb != lower ? nb->rank != h->rank + 1 : nb->rank != h->rank - 1))
+      throw std::runtime_error("not the neighbouring strip of the same partition");
+    if (nb->device != h->device) {
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, h->device, nb->device));
+      if (!can) throw std::runtime_error("the devices of neighbouring strips cannot access each other (no NVLink / P2P)");
+      cudaError_t e = cudaDeviceEnablePeerAccess(nb->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+      cudaGetLastError();
+    }
+  }
+  h->lower_base = lower ? lower->strip_alloc : nullptr;
+  h->upper_base = upper ? upper->strip_alloc : nullptr;
+  h->attached = true;
+  MAF_API_END(h)
+}
+
+// the strip's share of one calc_r_K, all on the handle's stream; the state is taken from d_xms / d_cps (device
+// pointers, full numnp x 3 / numnp x ndf arrays) or, if NULL, from the handle's resident state
+static void assemble_strip(maf_handle* h, const double* d_xms, const double* d_cps, double time, double dt,
+                           double bend_tm, int mode, double* d_rn_partial) {
+  if (h->nranks > 1 && !h->attached) throw std::runtime_error("attach the neighbouring strips first (maf_peer_attach)");
+  if (!d_xms || !d_cps) {
+    if (!h->state_resident) throw std::runtime_error("no resident state: pass device pointers or call maf_state_set");
+    d_xms = h->d_xms;
+    d_cps = h->d_cps;
+  }
+  cudaStream_t s = h->stream;
+  const long long step = ++h->step;
+  const long long spins = 50000000LL;   // ~10 s
+  long long* err = h->flags + 2;
+  // 1. our buffer may be zeroed only once the upper strip has pulled the previous step out of it
+  if (h->upper_base && step > 1) {
+    flag_kernel<<<1, 1, 0, s>>>(nullptr, 0, h->flags + 1, step - 1, err, spins);
+    h->launches += 1;
+  }
+  // 2. zero-fill + kernels of our elements (sums over our own elements; partial on the two interface node rows)
+  do_assemble_device(h, d_xms, d_cps, time, dt, bend_tm, mode, nullptr, nullptr, nullptr, s, false);
+  CU(cudaEventRecord(h->ev_x[0], s));
+  // 3. tell the upper strip that our partial sums are final; wait for the lower strip's
+  long long* upper_flags = h->upper_base ? reinterpret_cast<long long*>(h->upper_base) : nullptr;
+  long long* lower_flags = h->lower_base ? reinterpret_cast<long long*>(h->lower_base) : nullptr;
+  if (upper_flags || lower_flags) {
+    flag_kernel<<<1, 1, 0, s>>>(upper_flags ? upper_flags + 0 : nullptr, step, lower_flags ? h->flags + 0 : nullptr,
+                               step, err, spins);
+    h->launches += 1;
+  }
+  // 4. the interface belongs to us (the upper strip of the pair): add the lower strip's partial sums, read over NVLink
+  if (h->lower_base) {
+    const TouchedRange& L = h->lower;
+    const int64_t nr = L.eq_hi - h->eq_lo, nk = L.slot_hi - h->slot_lo;
+    const double* lr = reinterpret_cast<const double*>((const char*)h->lower_base + strip_r_offset()) + (h->eq_lo - L.eq_lo);
+    const double* lk = reinterpret_cast<const double*>((const char*)h->lower_base + strip_nz_offset(L)) + (h->slot_lo - L.slot_lo);
+    if (nr > 0) pull_add_kernel<<<(unsigned)std::min<int64_t>((nr + 255) / 256, h->sm_count * 4), 256, 0, s>>>(h->d_r + h->eq_lo, lr, nr);
+    if (nk > 0) pull_add_kernel<<<(unsigned)std::min<int64_t>((nk + 255) / 256, h->sm_count * 8), 256, 0, s>>>(h->d_nz + h->slot_lo, lk, nk);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    // 5. the lower strip may reuse its buffer
+    flag_kernel<<<1, 1, 0, s>>>(lower_flags + 1, step, nullptr, 0, err, spins);
+    h->launches += 1;
+  }
+  CU(cudaEventRecord(h->ev_x[1], s));
+  // 6. our share of sum(r^2): the rows we own (every row is owned by exactly one strip)
+  if (d_rn_partial) {
+    rnorm2_partial<<<256, 256, 0, s>>>(h->d_r + h->own_eq_lo, h->own_eq_hi - h->own_eq_lo, h->d_part);
+    rnorm2_final<<<1, 256, 0, s>>>(h->d_part, 256, d_rn_partial);
+    CU(cudaGetLastError());
+    h->launches += 2;
+  }
+}
+
+static void check_strip_error(maf_handle* h) {
+  long long e = 0;
+  CU(cudaMemcpyAsync(&e, h->flags + 2, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (e) throw std::runtime_error("a neighbouring strip did not arrive at step " + std::to_string(e) + " within the time-out");
+}
+
+int maf_assemble_strip(maf_handle* h, const double* d_xms, const double* d_cps, double time, double dt, double bend_tm,
+                       int scatter_mode, double* d_rnorm2_partial) {
+  MAF_API_BEGIN(h)
+  require_strip(h);
+  assemble_strip(h, d_xms, d_cps, time, dt, bend_tm, scatter_mode, d_rnorm2_partial ? d_rnorm2_partial : h->d_rn);
+  MAF_API_END(h)
+}
+
+// upload of the part of the state a strip reads: the node range [node_lo, node_hi) of every column
+static void upload_state_rows(maf_handle* h, const double* xms, const double* cps) {
+  const HostModel& M = h->M;
+  const size_t pitch = sizeof(double) * (size_t)M.numnp, width = sizeof(double) * (size_t)(h->node_hi - h->node_lo);
+  CU(cudaMemcpy2DAsync(h->d_xms + h->node_lo, pitch, xms + h->node_lo, pitch, width, 3, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpy2DAsync(h->d_cps + h->node_lo, pitch, cps + h->node_lo, pitch, width, (size_t)M.ndf,
+                       cudaMemcpyHostToDevice, h->stream));
+  h->state_resident = true;
+}
+
+int maf_assemble_strip_host(maf_handle* h, const double* xms, const double* cps, double time, double dt, double bend_tm,
+                            int scatter_mode, double* r_own, double* nzval_own, double* rnorm2_partial) {
+  MAF_API_BEGIN(h)
+  require_strip(h);
+  if (!r_own || !nzval_own) throw std::runtime_error("null buffer");
+  CU(cudaEventRecord(h->ev[0], h->stream));
+  if (xms && cps) upload_state_rows(h, xms, cps);
+  assemble_strip(h, nullptr, nullptr, time, dt, bend_tm, scatter_mode, h->d_rn);
+  cudaStream_t s = h->stream;
+  CU(cudaMemcpyAsync(r_own, h->d_r + h->own_eq_lo, sizeof(double) * (size_t)(h->own_eq_hi - h->own_eq_lo),
+                     cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(nzval_own, h->d_nz + h->own_slot_lo, sizeof(double) * (size_t)(h->own_slot_hi - h->own_slot_lo),
+                     cudaMemcpyDeviceToHost, s));
+  if (rnorm2_partial) CU(cudaMemcpyAsync(rnorm2_partial, h->d_rn, sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(h->ev[5], s));
+  check_strip_error(h);
+  CU(cudaEventElapsedTime(&h->ms[5], h->ev[0], h->ev[5]));
+  CU(cudaEventElapsedTime(&h->ms_exchange, h->ev_x[0], h->ev_x[1]));
+  MAF_API_END(h)
+}
+
+int maf_strip_timings(maf_handle* h, double* out2) {
+  MAF_API_BEGIN(h)
+  require_strip(h);
+  if (!out2) throw std::runtime_error("null output pointer");
+  CU(cudaEventSynchronize(h->ev_x[1]));
+  CU(cudaEventElapsedTime(&h->ms_exchange, h->ev_x[0], h->ev_x[1]));
+  out2[0] = h->ms_exchange;
+  out2[1] = (double)h->strip_bytes;
+  check_strip_error(h);
+  MAF_API_END(h)
+}
+
 int maf_set_element_range(maf_handle* h, int64_t el_first, int64_t el_last) {
   MAF_API_BEGIN(h)
+  if (h->strip) throw std::runtime_error("a strip handle holds one fixed element range");
   if (el_first < 1 || el_last > h->M.numel || el_first > el_last + 1)
     throw std::runtime_error("element range outside 1..numel");
   h->e0 = el_first - 1;

@@ -38,7 +38,7 @@ MAF_HD void boundary_gather(int lane, int nl, const Config& cfg, const Tables& T
     si[I_NODE + a] = (int32_t)node;
     si[I_MASK + a] = T.nodemask[node];
     for (int d = 0; d < 8; ++d) si[I_EQ + 8 * a + d] = d < cfg.ndf ? T.ID[(int64_t)cfg.ndf * node + d] : -1;
-    for (int b = 0; b < 9; ++b) si[I_PAIR + 9 * a + b] = T.elpair[81 * el + 9 * a + b];
+    for (int b = 0; b < 9; ++b) si[I_PAIR + 9 * a + b] = T.elpair[81 * (el - T.el0) + 9 * a + b];
   }
   // boundary basis (Mesh.jl:220-225, GpBasisFn.jl:271-273): BOTTOM/TOP = line1 x edge2, RIGHT/LEFT = edge1 x line2
   for (int k = lane; k < 81; k += nl) {

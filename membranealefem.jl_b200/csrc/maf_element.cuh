@@ -154,6 +154,8 @@ struct Tables {
   const int64_t* elbase;    // numel: smallest column pointer among the element's active (node, dof) columns
   int64_t numnp, numel;
   int num1el, nuel1;
+  int64_t el0;              // first element the per-element tables (elpair, elslot, elbase) hold: a strip handle
+                            // (maf_create_strip) keeps only its own elements; 0 otherwise
 };
 
 // shared-memory basis table: Phi[gp][c][a2][4] (node a = a1 + 3 a2 at 4 a2 + a1; the pad keeps the three values
@@ -337,7 +339,7 @@ MAF_HD void build_elslot(const Tables& T, int64_t el, int32_t* out /* MAF_SLOT_I
       if (J < 8) {
         const int64_t c = T.nodecol[8 * (int64_t)T.IX[9 * el + b] + J];
         if (c >= 0) {
-          const int64_t off = c - base + T.pairoff[(int64_t)T.elpair[81 * el + 9 * a + b] * 8 + J];
+          const int64_t off = c - base + T.pairoff[(int64_t)T.elpair[81 * (el - T.el0) + 9 * a + b] * 8 + J];
           if (off > 0x7fffff00LL) *overflow = 1;
           v = (int32_t)off;
         }
@@ -373,10 +375,10 @@ MAF_HD void gather_data_async(int tid, const Config& cfg, const Tables& T, const
   }
   {
     const int64_t el = ids[9];
-    const dbl2* src = reinterpret_cast<const dbl2*>(T.elslot + (size_t)MAF_SLOT_INTS * el);
+    const dbl2* src = reinterpret_cast<const dbl2*>(T.elslot + (size_t)MAF_SLOT_INTS * (el - T.el0));
     dbl2* dst = reinterpret_cast<dbl2*>(fr + cfg.o_slot);
     for (int k = tid; k < MAF_SLOT_INTS / 4; k += MAF_NT) async_copy16(dst + k, src + k);
-    if (tid == MAF_NT - 1) async_copy8(fr + cfg.o_po, T.elbase + el);
+    if (tid == MAF_NT - 1) async_copy8(fr + cfg.o_po, T.elbase + (el - T.el0));
   }
   const int u1 = ids[90], u2 = ids[91];
   if (T.utab) {   // precomputed per unique element (the same products, formed once on the host): straight copy

@@ -150,6 +150,7 @@ inline Tables host_tables(const HostModel& M) {
   T.uel1 = M.uel1.data(); T.uel2 = M.uel2.data(); T.line1 = M.line1.data(); T.line2 = M.line2.data();
   T.tdb = M.tdb.data(); T.colptr = M.sym.colptr.data(); T.elpair = M.sym.elpair.data();
   T.pairoff = M.sym.pairoff.data(); T.eq0 = M.sym.eq0.data(); T.nodecol = M.nodecol.data(); T.nodemask32 = M.nodemask32.data(); T.utab = M.utab.empty() ? nullptr : M.utab.data(); T.numnp = M.numnp; T.numel = M.numel; T.num1el = M.num1el; T.nuel1 = M.nuel1;
+  T.el0 = 0;
   return T;
 }
 // host copy of the per-element scatter maps (CPU emulation only; needs M.sym.elpair, i.e. before maf_create frees it)
@@ -208,6 +209,41 @@ inline void fill_gather_tables(const GatherHost& GH, GatherTables& G) {
   for (int c = 0; c < 64; ++c) { G.class_I[c] = GH.class_I[c]; G.class_J[c] = GH.class_J[c]; }
   G.sym_fill = GH.sym_fill;
   G.ncls = GH.ncls;
+}
+
+// ---- strips of element rows over several GPUs (the reference's per-task chunks, FiniteElement.jl:88-89) ----
+// What the elements [e0, e1) touch: nodes [node_lo, node_hi), equations [eq_lo, eq_hi), nnz slots [slot_lo, slot_hi) --
+// each contiguous because unknowns are numbered node-major (Mesh.jl:276-284).
+struct TouchedRange {
+  int64_t e0 = 0, e1 = 0, node_lo = 0, node_hi = 0, eq_lo = 0, eq_hi = 0, slot_lo = 0, slot_hi = 0;
+};
+inline TouchedRange touched_range(const HostModel& M, int64_t e0, int64_t e1) {
+  TouchedRange R;
+  R.e0 = e0; R.e1 = e1;
+  int64_t lo = M.numnp, hi = -1;
+  for (int64_t k = 9 * e0; k < 9 * e1; ++k) {
+    lo = std::min<int64_t>(lo, M.IX0[k]);
+    hi = std::max<int64_t>(hi, M.IX0[k]);
+  }
+  if (hi < 0) { lo = 0; hi = -1; }
+  R.node_lo = lo; R.node_hi = hi + 1;
+  int64_t eq_lo = M.nmdf, eq_hi = 0;
+  for (int64_t k = lo * M.ndf; k < (hi + 1) * M.ndf; ++k)
+    if (M.ID0[k] >= 0) { eq_lo = std::min<int64_t>(eq_lo, M.ID0[k]); eq_hi = std::max<int64_t>(eq_hi, M.ID0[k] + 1); }
+  if (eq_hi <= eq_lo) eq_lo = eq_hi = 0;
+  R.eq_lo = eq_lo; R.eq_hi = eq_hi;
+  R.slot_lo = M.sym.colptr[eq_lo]; R.slot_hi = M.sym.colptr[eq_hi];
+  return R;
+}
+// Strip `rank` of `nranks`: element rows [rank num2el / nranks, (rank + 1) num2el / nranks). Every strip needs at least
+// two element rows: a quadratic strip touches node rows e2 .. e2 + 2, so with thinner strips rank k and rank k + 2
+// would share a node row and the neighbour-only exchange would drop that overlap.
+inline TouchedRange strip_range(const HostModel& M, int rank, int nranks) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("strip rank outside 0..nranks-1");
+  if (nranks > 1 && M.num2el / nranks < 2)
+    throw std::runtime_error("the mesh has too few element rows for this many strips (each needs at least 2 rows)");
+  const int64_t r0 = ((int64_t)rank * M.num2el) / nranks, r1 = ((int64_t)(rank + 1) * M.num2el) / nranks;
+  return touched_range(M, r0 * M.num1el, r1 * M.num1el);
 }
 
 // processing order of the elements of a range: Z-order (Morton) over (e1, e2), so that the elements a wave of CTAs

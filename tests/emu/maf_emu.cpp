@@ -106,6 +106,19 @@ void emu_info(void* h, int64_t* o) {
   o[5] = c.task_rounds; o[6] = c.nblocks;
 }
 
+// strip of element rows `rank` of `nranks` as the library cuts it (maf_host.h::strip_range), 1-based inclusive:
+// [elements, rows of r touched, entries of nzval touched]; returns 1 when the partition is refused
+int emu_strip_range(void* h, int rank, int nranks, int64_t* o6) {
+  try {
+    const TouchedRange R = strip_range(((emu_model*)h)->M, rank, nranks);
+    o6[0] = R.e0 + 1; o6[1] = R.e1; o6[2] = R.eq_lo + 1; o6[3] = R.eq_hi; o6[4] = R.slot_lo + 1; o6[5] = R.slot_hi;
+    return 0;
+  } catch (std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
 // tangent schedule: per chunk [f, g, kind, fused, first, count], then chunk_slot[task_rounds * nwarps]
 int emu_chunks(void* h, int32_t* chunks6, int32_t* slots) {
   const Config& c = ((emu_model*)h)->M.cfg;

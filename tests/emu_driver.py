@@ -56,6 +56,13 @@ class Emu:
         return dict(zip(["asize", "smem_doubles", "ntasks", "nitems", "item_rounds", "task_rounds", "nblocks"],
                         o.tolist()))
 
+    def strip_range(self, rank, nranks):
+        """The library's own strip arithmetic (maf_host.h::strip_range): 1-based inclusive (elements, rows, slots)."""
+        o = np.zeros(6, dtype=np.int64)
+        if lib().emu_strip_range(self.h, rank, nranks, o.ctypes.data_as(C.POINTER(C.c_int64))):
+            raise RuntimeError(lib().emu_last_error().decode())
+        return (int(o[0]), int(o[1])), (int(o[2]), int(o[3])), (int(o[4]), int(o[5]))
+
     def chunks(self):
         """Tangent schedule: ([(f, g, kind, fused, first, count)], slots[round][warp])."""
         c6 = np.zeros(6 * 48, dtype=np.int32)

@@ -109,3 +109,28 @@ def test_partition_arithmetic():
     assert part.owned_rows(ranges, 2) == slice(200, 300)
     assert part.owned_slots(ranges, 0) == slice(0, 1000) and part.owned_slots(ranges, 1) == slice(1000, 2000)
     assert part.owned_slots(ranges, 2) == slice(2000, 3000)
+
+
+def test_library_strips_match_the_host_partition():
+    """The strip arithmetic behind the C ABI (maf_create_strip -> maf_host.h::strip_range, here through tests/emu) cuts
+    the same strips and touches the same ranges as host/partition.py; thin strips are refused by both."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mafb200 as maf
+    from emu_driver import Emu
+    part = maf.pkg.host.partition
+    p = maf.Params(motion=maf.ALEVB, scenario=maf.F_PULL, num1el=5, num2el=9, length=8.0, output=False)
+    mesh = maf.Mesh(p, pull_speed=0.5)
+    emu = Emu(mesh, p)
+    colptr, _ = emu.pattern()
+    for world in (1, 2, 3, 4):
+        prev_rows = prev_slots = None
+        for rank in range(world):
+            els, rows, slots = emu.strip_range(rank, world)
+            assert els == part.strip_elements(5, 9, world, rank)
+            assert (rows[0], rows[1], slots[0], slots[1]) == part.touched_ranges(mesh, colptr, *els)
+            if prev_rows is not None:       # neighbouring strips overlap (the two shared node rows), nothing else
+                assert prev_rows[0] < rows[0] <= prev_rows[1] < rows[1] and prev_slots[0] < slots[0] <= prev_slots[1] < slots[1]
+            prev_rows, prev_slots = rows, slots
+    with pytest.raises(RuntimeError, match="too few element rows"):
+        emu.strip_range(0, 5)
