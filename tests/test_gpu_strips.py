@@ -159,6 +159,8 @@ def test_one_process_per_strip_over_cuda_ipc(world):
         assert not isinstance(t[1], str), t[2]
     r = np.concatenate([t[1] for t in res])
     nz = np.concatenate([t[2] for t in res])
-    assert np.array_equal(nz, nz_w) and np.array_equal(r, r_w)      # deterministic path: same sums in the same order
+    # every strip sums its own elements in ascending element id and the interface adds (lower strip) + (upper strip):
+    # the same numbers as the whole mesh up to the association of that last addition; bitwise equal from step to step
+    assert np.abs(nz - nz_w).max() <= 1e-13 * np.abs(nz_w).max() and np.abs(r - r_w).max() <= 1e-13 * np.abs(r_w).max()
     for t in res:
         assert abs(t[3] - rn_w) <= 1e-12 * rn_w and t[4]
