@@ -7,8 +7,10 @@ A "step" is one pass of the hot path (one calc_r_K: area elements + Neumann boun
 synthetic flat F_PULL patch of BASELINE.json configs[4] (1001 x 1001 = 1 002 001 elements, ALEVB, perturbed state of
 SURVEY.md 8(d)5). `value` = elements/s with the inputs resident in HBM; `e2e` = the same call through the C ABI's
 host-buffer entry point (maf_assemble: H2D of xms/cps, D2H of r and nzval inside the timed region).
-N > 1 (torchrun): the patch is cut into N strips of element rows (strong scaling); after the kernels each rank
-exchanges only the interface rows/entries with its neighbours over NCCL and the residual norm is all-reduced.
+N > 1 (torchrun): the patch is cut into N strips of element rows (strong scaling), one strip handle per rank
+(maf_create_strip: sliced tables and result buffers); after its kernels the upper strip of every pair adds the lower
+strip's interface sums straight from its memory over NVLink (CUDA IPC peer loads, flag-ordered, inside the library)
+and the residual norm is all-reduced over NCCL.
 --impl reference times the CPU restatement of the reference algorithm (the reference itself is Julia, which this
 image does not have) on a bounded sample of the same workload with all host threads.
 
@@ -350,41 +352,47 @@ def run(a, out_stream):
     t_setup = time.perf_counter()
     mesh = maf.Mesh(p, pull_speed=0.5)
     xms, cps = maf.synthetic_state(mesh, p)
-    asm = maf.Assembler(mesh, p, device=local_rank)
+    free0 = torch.cuda.mem_get_info(dev)[0]
+    asm = maf.Assembler(mesh, p, device=local_rank, strip=(rank, world) if world > 1 else None)
     t_setup = time.perf_counter() - t_setup
     mode = maf.SCATTER_ATOMIC if a.scatter == "atomic" else maf.SCATTER_DETERMINISTIC
     dt = 0.5
 
-    # strips of element rows
-    part = maf.pkg.host.partition
+    # strips of element rows: one strip handle per rank, neighbours attached through CUDA IPC exports
+    sinfo = None
     if world > 1:
-        e_first, e_last = part.strip_elements(a.n, a.n, world, rank)
-        asm.set_element_range(e_first, e_last)
+        sinfo = asm.strip_info()
+        mine = torch.tensor(list(asm.peer_export()), dtype=torch.uint8, device=dev)
+        allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        asm.peer_attach(bytes(allh[rank - 1].cpu().tolist()) if rank > 0 else None,
+                        bytes(allh[rank + 1].cpu().tolist()) if rank + 1 < world else None)
     info = asm.range_info()
     my_elems = info["elements"][1] - info["elements"][0] + 1
 
     d_x = torch.from_numpy(np.ascontiguousarray(xms.T)).to(dev)
     d_c = torch.from_numpy(np.ascontiguousarray(cps.T)).to(dev)
-    d_r = torch.zeros(mesh.nmdf, dtype=torch.float64, device=dev)
-    d_k = torch.zeros(asm.nnz, dtype=torch.float64, device=dev)
+    d_r = d_k = None
+    if world == 1:
+        d_r = torch.zeros(mesh.nmdf, dtype=torch.float64, device=dev)
+        d_k = torch.zeros(asm.nnz, dtype=torch.float64, device=dev)
     d_n = torch.zeros(1, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    mem_used = free0 - torch.cuda.mem_get_info(dev)[0]
     # everything (kernels, interface copies, NCCL ops, timing events) is ordered on the handle's own stream
     torch.cuda.synchronize()
     ext = torch.cuda.ExternalStream(asm.stream(), device=dev)
     torch.cuda.set_stream(ext)
 
-    exchange = None
-    if world > 1:
-        mine = torch.tensor([info["rows"][0], info["rows"][1], info["slots"][0], info["slots"][1]], device=dev)
-        allr = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allr, mine)
-        exchange = part.InterfaceExchange(dist, [t.tolist() for t in allr], rank, d_r)
-
     def step():
-        asm.assemble_device(d_x.data_ptr(), d_c.data_ptr(), dt, dt, scatter_mode=mode, d_r=d_r.data_ptr(),
-                            d_nzval=d_k.data_ptr(), d_rnorm2=d_n.data_ptr() if world == 1 else None, stream=None)
-        if exchange is not None:
-            exchange(d_r, d_k, d_n)   # interface rows/entries to the neighbours (NCCL send/recv) + all-reduce |r|^2
+        if world == 1:
+            asm.assemble_device(d_x.data_ptr(), d_c.data_ptr(), dt, dt, scatter_mode=mode, d_r=d_r.data_ptr(),
+                                d_nzval=d_k.data_ptr(), d_rnorm2=d_n.data_ptr(), stream=None)
+        else:
+            # kernels of the strip, interface sums pulled from the lower neighbour's memory over NVLink, partial |r|^2
+            asm.assemble_strip(d_x.data_ptr(), d_c.data_ptr(), dt, dt, scatter_mode=mode,
+                               d_rnorm2_partial=d_n.data_ptr())
+            dist.all_reduce(d_n)          # the one NCCL collective of a step: the residual norm
 
     def barrier():
         torch.cuda.synchronize()
@@ -403,11 +411,13 @@ def run(a, out_stream):
     s_first = sampler.mark()
     l0 = asm.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms = []
+    kern_ms, xch_ms = [], []
     ev0.record()
     for _ in range(a.steps):
         step()
         kern_ms.append(asm.timings())
+        if world > 1:
+            xch_ms.append(asm.strip_timings()["exchange_ms"])
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -463,45 +473,62 @@ def run(a, out_stream):
         err = float(np.abs(hr.numpy() - d_r.cpu().numpy()).max())
         e2e["max_abs_diff_r_vs_device_path"] = err
     elif not a.no_e2e:
-        # N > 1: every rank uploads the state from pinned host memory, assembles its strip, exchanges the interface
-        # and copies the part of r / nzval it owns (each entry leaves exactly one GPU) to pinned host memory
-        ranges = [t.tolist() for t in allr]
-        own_r, own_k = part.owned_rows(ranges, rank), part.owned_slots(ranges, rank)
+        # N > 1, through the strip handle's host-buffer entry point (maf_assemble_strip_host): every rank uploads the
+        # node rows its strip reads from pinned host memory, assembles, takes part in the interface exchange and copies
+        # the rows of r / entries of nzval it OWNS (every entry leaves exactly one GPU) into pinned host memory
+        own_r = sinfo["own_rows"][1] - sinfo["own_rows"][0] + 1
+        own_k = sinfo["own_slots"][1] - sinfo["own_slots"][0] + 1
         hx = torch.from_numpy(np.ascontiguousarray(xms.T)).pin_memory()
         hc = torch.from_numpy(np.ascontiguousarray(cps.T)).pin_memory()
-        hr = torch.empty(own_r.stop - own_r.start, dtype=torch.float64).pin_memory()
-        hk = torch.empty(own_k.stop - own_k.start, dtype=torch.float64).pin_memory()
-        hn = torch.empty(1, dtype=torch.float64).pin_memory()
-
-        def e2e_step():
-            d_x.copy_(hx, non_blocking=True)
-            d_c.copy_(hc, non_blocking=True)
-            step()
-            hr.copy_(d_r[own_r], non_blocking=True)
-            hk.copy_(d_k[own_k], non_blocking=True)
-            hn.copy_(d_n, non_blocking=True)
-
+        hr = torch.empty(own_r, dtype=torch.float64).pin_memory()
+        hk = torch.empty(own_k, dtype=torch.float64).pin_memory()
+        xs, cs = hx.numpy().T, hc.numpy().T
+        rn_host = 0.0
         for _ in range(max(1, a.warmup)):
-            e2e_step()
+            asm.assemble_strip_host(xs, cs, dt, dt, scatter_mode=mode, r_own=hr.numpy(), nzval_own=hk.numpy())
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        tot = 0.0
         for _ in range(a.steps):
-            e2e_step()
-        e1.record()
+            _, _, rn_part = asm.assemble_strip_host(xs, cs, dt, dt, scatter_mode=mode, r_own=hr.numpy(),
+                                                    nzval_own=hk.numpy())
+            tot += asm.timings()["total_ms"]        # CUDA events on the handle's stream around the whole call
+            rn_host = rn_part
         barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        t = torch.tensor([tot], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot = float(t.item())
-        nb = torch.tensor([hr.numel() + hk.numel() + 1], dtype=torch.int64, device=dev)
+        rn_t = torch.tensor([rn_host], dtype=torch.float64, device=dev)
+        dist.all_reduce(rn_t)
+        nodes = info["nodes"][1] - info["nodes"][0] + 1
+        nb = torch.tensor([own_r + own_k + 1, (3 + mesh.ndf) * nodes], dtype=torch.int64, device=dev)
         dist.all_reduce(nb)
+        # host-link roofline of this box for this traffic: every rank copies its owned nzval slice to pinned host
+        # memory at the same time, nothing else running (what the e2e step cannot beat)
+        barrier()
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            asm.download(1, 0, sinfo["own_slots"][0], own_k, nz_out=hk.numpy())
+        torch.cuda.synchronize()
+        tl = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        link_s = float(tl.item()) / reps
+        kb = torch.tensor([own_k * 8], dtype=torch.int64, device=dev)
+        dist.all_reduce(kb)
+        link_gbs = float(kb.item()) / link_s / 1e9
+        e2e_s = tot / a.steps * 1e-3
         e2e = {"value": mesh.numel * a.steps / (tot * 1e-3) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": int((3 + mesh.ndf) * mesh.numnp * 8) * world,
-               "d2h_bytes_per_step": int(nb.item()) * 8, "ms_per_step": tot / a.steps,
-               "note": "per rank: H2D xms+cps from pinned host memory, strip assembly, NCCL interface exchange, D2H "
-                       "of the owned rows of r / entries of nzval into pinned host memory (every entry leaves "
-                       "exactly one GPU); CUDA events on the handle's stream, max over ranks",
-               "rnorm2_host": float(hn.item())}
+               "h2d_bytes_per_step": int(nb[1].item()) * 8, "d2h_bytes_per_step": int(nb[0].item()) * 8,
+               "ms_per_step": tot / a.steps,
+               "note": "per rank, maf_assemble_strip_host: H2D of the node rows the strip reads (pinned host memory), "
+                       "strip assembly, interface sums over NVLink, D2H of the owned rows of r / entries of nzval "
+                       "into pinned host memory (every entry leaves exactly one GPU); CUDA events on the handle's "
+                       "stream around the call, max over ranks",
+               "rnorm2_host": float(rn_t.item()),
+               "host_link_roofline": {"aggregate_d2h_gbs": link_gbs, "ms_for_nzval": link_s * 1e3,
+                                      "e2e_fraction_of_link_roofline": link_s / e2e_s,
+                                      "how": f"{world} ranks copy their owned nzval slices to pinned host memory "
+                                             "concurrently, nothing else running; max over ranks"}}
 
     if rank != 0:
         if world > 1:
@@ -562,9 +589,12 @@ def run(a, out_stream):
                       "numel": mesh.numel, "numnp": mesh.numnp, "nmdf": mesh.nmdf, "nnz": asm.nnz,
                       "pattern": "P_blk", "scatter": a.scatter, "elements_per_rank": my_elems,
                       "l2": "no flush: each step streams r + nzval (%.1f GB) >> 126 MB L2" % (asm.nnz * 8 / 1e9),
-                      "parallelism": (f"{world} strips of element rows; NCCL send/recv of interface rows + all-reduce "
-                                      f"of the residual norm ({exchange.bytes_per_step()} B/step/rank)")
+                      "parallelism": (f"{world} strips of element rows, one strip handle per rank (maf_create_strip); "
+                                      f"interface sums read from the lower neighbour's memory over NVLink (CUDA IPC "
+                                      f"peer loads inside the library, {float(np.mean(xch_ms)):.3f} ms per step on "
+                                      f"rank 0 incl. waiting for the neighbour); NCCL all-reduce of the residual norm")
                       if world > 1 else "single GPU",
+                      "device_mem_used_gb_rank0": mem_used / 1e9,
                       "setup_s": t_setup, "kernel": asm.kernel_info()},
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
            "newton_iteration": newton, "parity_spot": spot, "rnorm2": rnorm2}

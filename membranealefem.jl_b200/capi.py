@@ -227,9 +227,12 @@ class Assembler:
         self._check(self.L.maf_pattern_columns(self.h, col_first, col_last, _ptr(rowval, C.c_int64)))
         return rowval
 
-    def download(self, r_first=1, r_count=0, nz_first=1, nz_count=0):
-        """Slices (1-based starts) of the handle's device-resident r / nzval after assemble_device."""
-        r, nz = np.empty(r_count), np.empty(nz_count)
+    def download(self, r_first=1, r_count=0, nz_first=1, nz_count=0, r_out=None, nz_out=None):
+        """Slices (1-based starts) of the handle's device-resident r / nzval after assemble_device; r_out / nz_out:
+        caller-owned (e.g. page-locked) destination arrays."""
+        r = np.empty(r_count) if r_out is None else r_out
+        nz = np.empty(nz_count) if nz_out is None else nz_out
+        assert r.size >= r_count and nz.size >= nz_count
         self._check(self.L.maf_download(self.h, r_first, r_count, _ptr(r, C.c_double), nz_first, nz_count,
                                         _ptr(nz, C.c_double)))
         return r, nz
