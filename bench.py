@@ -411,15 +411,17 @@ def run(a, out_stream):
     s_first = sampler.mark()
     l0 = asm.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms, xch_ms = [], []
     ev0.record()
-    for _ in range(a.steps):
+    for _ in range(a.steps):          # no host synchronisation inside the timed region
         step()
-        kern_ms.append(asm.timings())
-        if world > 1:
-            xch_ms.append(asm.strip_timings()["exchange_ms"])
     ev1.record()
     barrier()
+    # device time of the dominant kernel in every launch of the timed region (event ring inside the library), and the
+    # other parts of the LAST step
+    n_ring = min(a.steps, 64)
+    area_ms = asm.area_kernel_times(n_ring)
+    last = asm.timings()
+    xch_ms = [asm.strip_timings()["exchange_ms"]] if world > 1 else []
     ms = ev0.elapsed_time(ev1)
     launches = asm.launch_count() - l0
     if world > 1:
@@ -542,8 +544,10 @@ def run(a, out_stream):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    area = float(np.mean([k["area_ms"] for k in kern_ms]))
-    other = {k: float(np.mean([t[k] for t in kern_ms])) for k in ("zero_ms", "bdry_ms", "gather_ms")}
+    area = float(np.mean(area_ms))
+    other = {k: float(last[k]) for k in ("zero_ms", "bdry_ms", "gather_ms")}
+    other["note"] = ("last step; atomics path: the Neumann boundary kernels run beside the area kernel on a second "
+                     "stream (bdry_ms = what is left to wait for)")
     fp64_peak = maf.fp64_peak_tflops(local_rank)
     ach_gbs = my_elems * B_EL[a.motion] / (area * 1e-3) / 1e9
     ach_tf = my_elems * F_EL[a.motion] / (area * 1e-3) / 1e12

@@ -144,6 +144,9 @@ int maf_sync(maf_handle* h);
  * only set by maf_assemble. And the number of kernels this handle has launched so far. */
 int maf_timings(maf_handle* h, double* out7);
 int maf_launch_count(maf_handle* h, int64_t* n);
+/* Device time (ms, CUDA events on the launching stream) of the area-element kernel in each of the last n assemblies,
+ * oldest first (n <= 64): read once after a timed region, so the region itself needs no host synchronisation. */
+int maf_area_kernel_times(maf_handle* h, double* out_ms, int64_t n);
 
 /* Area-element kernel configuration actually used: out[0] threads per CTA, out[1] elements per CTA,
  * out[2] dynamic shared memory bytes per CTA, out[3] resident CTAs per SM, out[4] SM count. */

@@ -48,7 +48,7 @@ EXPORTS = ["maf_create", "maf_destroy", "maf_last_error", "maf_nnz", "maf_patter
            "maf_assemble_resident", "maf_elem_v_residuals", "maf_host_register", "maf_host_unregister",
            "maf_colptr", "maf_pattern_columns", "maf_download", "maf_create_strip", "maf_strip_info",
            "maf_peer_attach_local", "maf_peer_export", "maf_peer_attach", "maf_assemble_strip",
-           "maf_assemble_strip_host", "maf_strip_timings"]
+           "maf_assemble_strip_host", "maf_strip_timings", "maf_area_kernel_times"]
 
 
 def load_library(path=None):
@@ -89,6 +89,7 @@ def load_library(path=None):
     L.maf_sync.argtypes = [C.c_void_p]
     L.maf_timings.argtypes = [C.c_void_p, _F64P]
     L.maf_launch_count.argtypes = [C.c_void_p, _I64P]
+    L.maf_area_kernel_times.argtypes = [C.c_void_p, _F64P, C.c_int64]
     L.maf_kernel_info.argtypes = [C.c_void_p, _I64P]
     L.maf_chunk_plan.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     L.maf_host_register.argtypes = [C.c_void_p, C.c_int64]
@@ -309,6 +310,12 @@ class Assembler:
         o = np.zeros(7)
         self._check(self.L.maf_timings(self.h, _ptr(o, C.c_double)))
         return dict(zip(["h2d_ms", "area_ms", "bdry_ms", "gather_ms", "d2h_ms", "total_ms", "zero_ms"], o.tolist()))
+
+    def area_kernel_times(self, n):
+        """Device ms of the area kernel in each of the last n assemblies (oldest first, n <= 64)."""
+        o = np.zeros(int(n))
+        self._check(self.L.maf_area_kernel_times(self.h, _ptr(o, C.c_double), int(n)))
+        return o
 
     def launch_count(self):
         n = C.c_int64()

@@ -382,7 +382,15 @@ struct maf_handle {
   long long step = 0;                 // assemblies done (the flags carry it)
   cudaEvent_t ev_x[4] = {};
   float ms_exchange = 0.f;
+  // ring of event pairs around the area kernel of the last MAF_RING assemblies: per-launch device times of a whole
+  // timed region can be read afterwards, with no host synchronisation between the steps (maf_area_kernel_times)
+  cudaEvent_t ring_a[64] = {}, ring_b[64] = {};
+  long long ring_n = 0;
+  // the Neumann boundary kernels (atomics path) run beside the area kernel on a second stream
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_side[2] = {};
 };
+#define MAF_RING 64
 // layout of a strip allocation: 256 bytes of flags, the r slice, the nzval slice (each padded to 256 bytes)
 static size_t strip_r_offset() { return 256; }
 static size_t strip_nz_offset(const TouchedRange& R) {
@@ -572,9 +580,29 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
     st = StageSink{h->d_kel, h->d_rel, h->nij};
   }
   CU(cudaEventRecord(h->ev[6], s));
+  // atomics path: the (tiny) Neumann boundary kernels only add into r / nzval, in any order: they run on a second
+  // stream beside the area kernel instead of after it
+  const bool side = mode == MAF_SCATTER_ATOMIC && M.n_neu > 0 && h->side_stream;
+  if (side) {
+    CU(cudaStreamWaitEvent(h->side_stream, h->ev[6], 0));
+    for (int bc = 0; bc < M.n_neu; ++bc) {
+      const int n = M.b_offs[bc + 1] - M.b_offs[bc];
+      if (n == 0) continue;
+      const double fval = neumann_value(M.b_type[bc], M.b_val[bc], time, bend_tm);
+      const int gb = std::min((n + 3) / 4, h->sm_count * 8);
+      boundary_kernel<<<gb, 128, 0, h->side_stream>>>(M.cfg, h->T, h->BT, bc, fval, dt, d_xms, d_r, d_nz, -1, 1, h->e0, h->e1);
+      CU(cudaGetLastError());
+      h->launches += 1;
+    }
+    CU(cudaEventRecord(h->ev_side[0], h->side_stream));
+  }
   if (ne > 0) {
+    const int q = (int)(h->ring_n % MAF_RING);
+    CU(cudaEventRecord(h->ring_a[q], s));
     kern<<<grid, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, h->d_order, h->e0, h->e1);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ring_b[q], s));
+    h->ring_n += 1;
     h->launches += 1;
   }
   CU(cudaEventRecord(h->ev[2], s));
@@ -589,7 +617,8 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
     h->launches += 2;
   }
   CU(cudaEventRecord(h->ev[3], s));
-  for (int bc = 0; bc < M.n_neu; ++bc) {
+  if (side) CU(cudaStreamWaitEvent(s, h->ev_side[0], 0));
+  for (int bc = 0; bc < M.n_neu && !side; ++bc) {
     const int n = M.b_offs[bc + 1] - M.b_offs[bc];
     if (n == 0) continue;
     const double fval = neumann_value(M.b_type[bc], M.b_val[bc], time, bend_tm);
@@ -693,7 +722,10 @@ static int create_handle(maf_handle** out, const maf_mesh_desc* mesh, const maf_
     compute_ranges(h);
 
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
     for (int k = 0; k < 8; ++k) CU(cudaEventCreate(&h->ev[k]));
+    for (int k = 0; k < MAF_RING; ++k) { CU(cudaEventCreate(&h->ring_a[k])); CU(cudaEventCreate(&h->ring_b[k])); }
+    for (int k = 0; k < 2; ++k) CU(cudaEventCreateWithFlags(&h->ev_side[k], cudaEventDisableTiming));
 
     h->T.IX = upload(h, M.IX0.data(), M.IX0.size());
     h->T.ID = upload(h, M.ID0.data(), M.ID0.size());
@@ -809,6 +841,13 @@ int maf_destroy(maf_handle* h) {
   if (h->lower_base && h->lower_ipc) cudaIpcCloseMemHandle(h->lower_base);
   if (h->upper_base && h->upper_ipc) cudaIpcCloseMemHandle(h->upper_base);
   if (h->strip_alloc) cudaFree(h->strip_alloc);
+  if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
+  for (int k = 0; k < MAF_RING; ++k) {
+    if (h->ring_a[k]) cudaEventDestroy(h->ring_a[k]);
+    if (h->ring_b[k]) cudaEventDestroy(h->ring_b[k]);
+  }
+  for (int k = 0; k < 2; ++k)
+    if (h->ev_side[k]) cudaEventDestroy(h->ev_side[k]);
   for (int k = 0; k < 4; ++k)
     if (h->ev_x[k]) cudaEventDestroy(h->ev_x[k]);
   for (void* p : h->allocs) cudaFree(p);
@@ -1148,6 +1187,20 @@ int maf_timings(maf_handle* h, double* out7) {
     CU(cudaEventElapsedTime(&h->ms[2], h->ev[3], h->ev[4]));
   }
   for (int k = 0; k < 7; ++k) out7[k] = h->ms[k];
+  MAF_API_END(h)
+}
+
+int maf_area_kernel_times(maf_handle* h, double* out_ms, int64_t n) {
+  MAF_API_BEGIN(h)
+  if (!out_ms || n < 0) throw std::runtime_error("null output pointer");
+  if (n > MAF_RING || n > h->ring_n) throw std::runtime_error("more launches requested than the ring holds");
+  for (int64_t k = 0; k < n; ++k) {   // out[0] = oldest of the last n launches
+    const int q = (int)((h->ring_n - n + k) % MAF_RING);
+    CU(cudaEventSynchronize(h->ring_b[q]));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ring_a[q], h->ring_b[q]));
+    out_ms[k] = ms;
+  }
   MAF_API_END(h)
 }
 
