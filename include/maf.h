@@ -149,8 +149,9 @@ int maf_launch_count(maf_handle* h, int64_t* n);
 int maf_area_kernel_times(maf_handle* h, double* out_ms, int64_t n);
 
 /* Area-element kernel configuration actually used: out[0] threads per CTA, out[1] elements per CTA,
- * out[2] dynamic shared memory bytes per CTA, out[3] resident CTAs per SM, out[4] SM count. */
-int maf_kernel_info(maf_handle* h, int64_t* out5);
+ * out[2] dynamic shared memory bytes per CTA, out[3] resident CTAs per SM, out[4] SM count, out[5] number of distinct
+ * element scatter maps (elements with equal maps share one: a few hundred on a structured 10^6-element patch). */
+int maf_kernel_info(maf_handle* h, int64_t* out6);
 
 /* The static plan of the area kernel's contraction phase as text: "c,c,c/c,c/..." = the chunk ids (<= 32 tangent
  * tasks of one block each) that every warp of the CTA executes, in order. The environment variable MAF_PLAN (same

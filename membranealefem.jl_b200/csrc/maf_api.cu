@@ -18,6 +18,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "maf_host.h"
@@ -154,13 +155,20 @@ area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __
 #endif
 }
 
-// One-time (maf_create): the scatter map of every element, one CTA per element (maf_element.cuh::build_elslot).
+// One-time (maf_create): the scatter maps (maf_element.cuh::build_elslot), one CTA per element, in three passes that
+// never materialise one map per element (2.9 KB each): MODE 0 hashes every element's map, the host groups equal
+// hashes into classes, MODE 1 writes the map of each class's representative element, MODE 2 re-derives every
+// element's map and compares it with its class's (a hash collision is reported, never silently accepted).
+template <int MODE>
 __global__ void __launch_bounds__(128)
-build_elslot_kernel(const Tables T, int32_t* __restrict__ elslot, int64_t* __restrict__ elbase, int* __restrict__ overflow) {
+build_elslot_kernel(const Tables T, const int32_t* __restrict__ rep_el /* MODE 1: representative element per class */,
+                    int32_t* __restrict__ elslot, int64_t* __restrict__ elbase, unsigned long long* __restrict__ hash,
+                    int* __restrict__ flags /* [0] overflow, [1] mismatch */) {
   __shared__ long long s_col[72];
   __shared__ long long s_base;
-  const int64_t el = T.el0 + blockIdx.x;   // (a strip handle builds the maps of its own elements only)
+  __shared__ unsigned long long s_hash[128];
   const int tid = threadIdx.x;
+  const int64_t el = MODE == 1 ? (int64_t)rep_el[blockIdx.x] : T.el0 + blockIdx.x;
   if (tid < 72) s_col[tid] = T.nodecol[8 * (int64_t)T.IX[9 * el + (tid >> 3)] + (tid & 7)];
   __syncthreads();
   if (tid == 0) {
@@ -168,10 +176,12 @@ build_elslot_kernel(const Tables T, int32_t* __restrict__ elslot, int64_t* __res
     for (int k = 0; k < 72; ++k)
       if (s_col[k] >= 0 && (base < 0 || s_col[k] < base)) base = s_col[k];
     s_base = base < 0 ? 0 : base;
-    elbase[el - T.el0] = s_base;
+    if (MODE == 0) elbase[el - T.el0] = s_base;
   }
   __syncthreads();
   const long long base = s_base;
+  unsigned long long hsum = 0;
+  const int32_t* cls = MODE == 2 ? T.elslot + (size_t)MAF_SLOT_INTS * T.elclass[el - T.el0] : nullptr;
   for (int k = tid; k < MAF_SLOT_INTS; k += 128) {
     int32_t v = -1;
     if (k < 729) {
@@ -180,12 +190,29 @@ build_elslot_kernel(const Tables T, int32_t* __restrict__ elslot, int64_t* __res
         const long long c = s_col[8 * b + J];
         if (c >= 0) {
           const long long off = c - base + T.pairoff[(int64_t)T.elpair[81 * (el - T.el0) + 9 * a + b] * 8 + J];
-          if (off > 0x7fffff00LL) *overflow = 1;
+          if (off > 0x7fffff00LL) flags[0] = 1;
           v = (int32_t)off;
         }
       }
     }
-    elslot[(size_t)MAF_SLOT_INTS * (el - T.el0) + k] = v;
+    if (MODE == 0) {   // position-dependent mix, summed over the map (order independent)
+      unsigned long long x = ((unsigned long long)(unsigned)v << 20) ^ (unsigned long long)(k + 1) * 0x9E3779B97F4A7C15ull;
+      x ^= x >> 31; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 29; x *= 0x94D049BB133111EBull; x ^= x >> 32;
+      hsum += x;
+    } else if (MODE == 1) {
+      elslot[(size_t)MAF_SLOT_INTS * blockIdx.x + k] = v;
+    } else if (cls[k] != v) {
+      flags[1] = 1;
+    }
+  }
+  if (MODE == 0) {
+    s_hash[tid] = hsum;
+    __syncthreads();
+    for (int w = 64; w > 0; w >>= 1) {
+      if (tid < w) s_hash[tid] += s_hash[tid + w];
+      __syncthreads();
+    }
+    if (tid == 0) hash[el - T.el0] = s_hash[0];
   }
 }
 
@@ -386,6 +413,7 @@ struct maf_handle {
   // timed region can be read afterwards, with no host synchronisation between the steps (maf_area_kernel_times)
   cudaEvent_t ring_a[64] = {}, ring_b[64] = {};
   long long ring_n = 0;
+  int64_t n_slot_classes = 0;         // distinct scatter maps (Tables::elslot rows)
   // the Neumann boundary kernels (atomics path) run beside the area kernel on a second stream
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_side[2] = {};
@@ -746,19 +774,53 @@ static int create_handle(maf_handle** out, const maf_mesh_desc* mesh, const maf_
     h->T.nodemask32 = upload(h, M.nodemask32.data(), M.nodemask32.size());
     h->T.utab = M.utab.empty() ? nullptr : upload(h, M.utab.data(), M.utab.size());
     h->T.numnp = M.numnp; h->T.numel = M.numel; h->T.num1el = M.num1el; h->T.nuel1 = M.nuel1;
-    {   // per-element scatter maps, built on the device from the tables above (2.9 KB per element)
-      int32_t* d_slot = dalloc<int32_t>(h, (size_t)MAF_SLOT_INTS * nel_tab);
+    {   // scatter maps, built on the device from the tables above and merged into classes of equal maps
       int64_t* d_base = dalloc<int64_t>(h, (size_t)nel_tab);
-      int* d_ovf = dalloc<int>(h, 1);
-      CU(cudaMemsetAsync(d_ovf, 0, sizeof(int), h->stream));
-      if (nel_tab > 0) build_elslot_kernel<<<(unsigned)nel_tab, 128, 0, h->stream>>>(h->T, d_slot, d_base, d_ovf);
-      CU(cudaGetLastError());
-      int ovf = 0;
-      CU(cudaMemcpyAsync(&ovf, d_ovf, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      CU(cudaStreamSynchronize(h->stream));
-      if (ovf) throw std::runtime_error("scatter map offset exceeds 32 bits (an element spans more than 2^31 stored entries)");
-      h->T.elslot = d_slot;
+      int32_t* d_class = dalloc<int32_t>(h, (size_t)nel_tab);
+      int* d_flags = dalloc<int>(h, 2);
+      unsigned long long* d_hash = nullptr;
+      CU(cudaMalloc(&d_hash, sizeof(unsigned long long) * (size_t)std::max<int64_t>(nel_tab, 1)));
+      CU(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), h->stream));
       h->T.elbase = d_base;
+      h->T.elclass = d_class;
+      if (nel_tab > 0)
+        build_elslot_kernel<0><<<(unsigned)nel_tab, 128, 0, h->stream>>>(h->T, nullptr, nullptr, d_base, d_hash, d_flags);
+      CU(cudaGetLastError());
+      std::vector<unsigned long long> hh((size_t)nel_tab);
+      CU(cudaMemcpyAsync(hh.data(), d_hash, sizeof(unsigned long long) * (size_t)nel_tab, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      cudaFree(d_hash);
+      std::vector<int32_t> cls((size_t)nel_tab), rep;
+      {
+        std::unordered_map<unsigned long long, int32_t> seen;
+        seen.reserve(4096);
+        for (int64_t k = 0; k < nel_tab; ++k) {
+          auto it = seen.find(hh[(size_t)k]);
+          if (it == seen.end()) {
+            it = seen.emplace(hh[(size_t)k], (int32_t)rep.size()).first;
+            rep.push_back((int32_t)(h->T.el0 + k));
+          }
+          cls[(size_t)k] = it->second;
+        }
+      }
+      h->n_slot_classes = (int64_t)rep.size();
+      int32_t* d_rep = nullptr;
+      CU(cudaMalloc(&d_rep, sizeof(int32_t) * std::max<size_t>(rep.size(), 1)));
+      int32_t* d_slot = dalloc<int32_t>(h, (size_t)MAF_SLOT_INTS * std::max<size_t>(rep.size(), 1));
+      h->T.elslot = d_slot;
+      CU(cudaMemcpyAsync(d_rep, rep.data(), sizeof(int32_t) * rep.size(), cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(d_class, cls.data(), sizeof(int32_t) * cls.size(), cudaMemcpyHostToDevice, h->stream));
+      if (!rep.empty()) {
+        build_elslot_kernel<1><<<(unsigned)rep.size(), 128, 0, h->stream>>>(h->T, d_rep, d_slot, nullptr, nullptr, d_flags);
+        build_elslot_kernel<2><<<(unsigned)nel_tab, 128, 0, h->stream>>>(h->T, nullptr, nullptr, nullptr, nullptr, d_flags);
+      }
+      CU(cudaGetLastError());
+      int fl[2] = {0, 0};
+      CU(cudaMemcpyAsync(fl, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      cudaFree(d_rep);
+      if (fl[0]) throw std::runtime_error("scatter map offset exceeds 32 bits (an element spans more than 2^31 stored entries)");
+      if (fl[1]) throw std::runtime_error("internal: two different scatter maps share a hash");
     }
     h->BT.edge1 = upload(h, M.edge1.data(), M.edge1.size());
     h->BT.edge2 = upload(h, M.edge2.data(), M.edge2.size());
@@ -1090,6 +1152,8 @@ int maf_elem_v_residuals(maf_handle* h, const int64_t* el_ids, int64_t n, double
   std::vector<int32_t> els((size_t)n);
   for (int64_t k = 0; k < n; ++k) {
     if (el_ids[k] < 1 || el_ids[k] > M.numel) throw std::runtime_error("element id outside 1..numel");
+    if (h->strip && (el_ids[k] - 1 < h->e0 || el_ids[k] - 1 >= h->e1))
+      throw std::runtime_error("element outside this strip (a strip handle holds the tables of its own elements)");
     els[(size_t)k] = (int32_t)(el_ids[k] - 1);
   }
   int32_t* d_els = nullptr;
@@ -1211,10 +1275,11 @@ int maf_launch_count(maf_handle* h, int64_t* n) {
   MAF_API_END(h)
 }
 
-int maf_kernel_info(maf_handle* h, int64_t* out5) {
+int maf_kernel_info(maf_handle* h, int64_t* out5 /* 6 values */) {
   MAF_API_BEGIN(h)
   if (!out5) throw std::runtime_error("null output pointer");
   out5[0] = MAF_NT; out5[1] = 1; out5[2] = (int64_t)h->smem_bytes; out5[3] = h->ctas_per_sm; out5[4] = h->sm_count;
+  out5[5] = h->n_slot_classes;
   MAF_API_END(h)
 }
 

@@ -150,7 +150,10 @@ struct Tables {
   const int64_t* nodecol;   // numnp x 8: colptr[ID[J, node]], -1 for inactive dofs
   const int32_t* nodemask32;  // nodemask as int32 (the granularity of an asynchronous copy)
   const double* utab;       // (nuel1*nuel2) x BASIS_DOUBLES precomputed basis blocks, or NULL (built per element)
-  const int32_t* elslot;    // numel x MAF_SLOT_INTS: scatter map of every element (build_elslot), relative to elbase
+  const int32_t* elslot;    // nclasses x MAF_SLOT_INTS: scatter maps (build_elslot), relative to elbase. Elements whose
+                            // maps coincide share one (translation classes: on a structured patch every element
+                            // away from Dirichlet nodes and mesh edges has the same map), so the table lives in L2
+  const int32_t* elclass;   // numel: the element's class = its row of elslot
   const int64_t* elbase;    // numel: smallest column pointer among the element's active (node, dof) columns
   int64_t numnp, numel;
   int num1el, nuel1;
@@ -255,7 +258,7 @@ MAF_HD void build_basis_block(int tid, int nt, const double* l1, const double* l
 //   level 1 (gather_ids_async)   node ids, pair ids, unique-element ids of element k + 2G -> ids buffer
 //   level 2 (gather_data_async)  nodal data, equation numbers, column pointers, pairoff rows, basis block of
 //                                element k + G (addresses from the ids buffer filled one iteration earlier)
-// ids buffer (int32): [0,9) node ids | 9: element id | 90, 91: unique-element id per direction
+// ids buffer (int32): [0,9) node ids | 9: element id | 10: scatter-map class | 90, 91: unique-element id per direction
 #define MAF_IDS_INTS 92
 #define MAF_IDS_DOUBLES 46
 MAF_HD void async_copy4(void* sdst, const void* gsrc) {
@@ -306,6 +309,7 @@ MAF_HD void gather_init(int tid, const Config& cfg, double* fr) {
 MAF_HD void gather_ids_async(int tid, const Tables& T, int64_t el, int32_t* ids) {
   if (tid < 9) async_copy4(ids + tid, T.IX + 9 * el + tid);
   else if (tid == 9) ids[9] = (int32_t)el;   // read by gather_data_async one iteration (and a barrier) later
+  else if (tid == 10) async_copy4(ids + 10, T.elclass + (el - T.el0));
   else if (tid == 90) async_copy4(ids + 90, T.uel1 + (el % T.num1el));
   else if (tid == 91) async_copy4(ids + 91, T.uel2 + (el / T.num1el));
 }
@@ -375,7 +379,7 @@ MAF_HD void gather_data_async(int tid, const Config& cfg, const Tables& T, const
   }
   {
     const int64_t el = ids[9];
-    const dbl2* src = reinterpret_cast<const dbl2*>(T.elslot + (size_t)MAF_SLOT_INTS * (el - T.el0));
+    const dbl2* src = reinterpret_cast<const dbl2*>(T.elslot + (size_t)MAF_SLOT_INTS * ids[10]);
     dbl2* dst = reinterpret_cast<dbl2*>(fr + cfg.o_slot);
     for (int k = tid; k < MAF_SLOT_INTS / 4; k += MAF_NT) async_copy16(dst + k, src + k);
     if (tid == MAF_NT - 1) async_copy8(fr + cfg.o_po, T.elbase + (el - T.el0));

@@ -26,6 +26,7 @@ struct HostModel {
   std::vector<int64_t> nodecol;      // column pointers per (node, dof) (Tables)
   std::vector<int32_t> elslot;       // per-element scatter maps, HOST copy: only built for the CPU emulation of the
   std::vector<int64_t> elbase;       // kernels (tests/emu); the library builds them on the device (build_elslot_kernel)
+  std::vector<int32_t> elclass;      // host copy: one class per element (the library merges equal maps on the device)
   std::vector<int32_t> nodemask32;
   std::vector<int32_t> b_elems, b_offs, b_bdry, b_type;
   std::vector<double> b_val;
@@ -146,6 +147,7 @@ inline Tables host_tables(const HostModel& M) {
   Tables T;
   T.elslot = M.elslot.empty() ? nullptr : M.elslot.data();
   T.elbase = M.elbase.empty() ? nullptr : M.elbase.data();
+  T.elclass = M.elclass.empty() ? nullptr : M.elclass.data();
   T.IX = M.IX0.data(); T.ID = M.ID0.data(); T.nodemask = M.sym.nodemask.data();
   T.uel1 = M.uel1.data(); T.uel2 = M.uel2.data(); T.line1 = M.line1.data(); T.line2 = M.line2.data();
   T.tdb = M.tdb.data(); T.colptr = M.sym.colptr.data(); T.elpair = M.sym.elpair.data();
@@ -157,6 +159,8 @@ inline Tables host_tables(const HostModel& M) {
 inline void build_host_elslot(HostModel& M) {
   M.elslot.assign((size_t)MAF_SLOT_INTS * M.numel, -1);
   M.elbase.assign((size_t)M.numel, 0);
+  M.elclass.resize((size_t)M.numel);
+  for (int64_t e = 0; e < M.numel; ++e) M.elclass[(size_t)e] = (int32_t)e;
   Tables T = host_tables(M);
   int overflow = 0;
   for (int64_t e = 0; e < M.numel; ++e)
