@@ -150,8 +150,10 @@ int maf_area_kernel_times(maf_handle* h, double* out_ms, int64_t n);
 
 /* Area-element kernel configuration actually used: out[0] threads per CTA, out[1] elements per CTA,
  * out[2] dynamic shared memory bytes per CTA, out[3] resident CTAs per SM, out[4] SM count, out[5] number of distinct
- * element scatter maps (elements with equal maps share one: a few hundred on a structured 10^6-element patch). */
-int maf_kernel_info(maf_handle* h, int64_t* out6);
+ * element scatter maps (elements with equal maps share one: a few hundred on a structured 10^6-element patch),
+ * out[6] assemblies replayed from a captured CUDA graph so far (meshes of <= 16384 elements assembling into the
+ * handle's own buffers: their ~10 launches are bound by the host's launch rate; MAF_NO_GRAPH=1 disables it). */
+int maf_kernel_info(maf_handle* h, int64_t* out7);
 
 /* The static plan of the area kernel's contraction phase as text: "c,c,c/c,c/..." = the chunk ids (<= 32 tangent
  * tasks of one block each) that every warp of the CTA executes, in order. The environment variable MAF_PLAN (same

@@ -414,6 +414,11 @@ struct maf_handle {
   cudaEvent_t ring_a[64] = {}, ring_b[64] = {};
   long long ring_n = 0;
   int64_t n_slot_classes = 0;         // distinct scatter maps (Tables::elslot rows)
+  // small meshes: the launch sequence of an assembly, captured once per key and replayed (do_assemble_device)
+  struct Graph { std::vector<double> key; cudaGraphExec_t exec = nullptr; int launches = 0; };
+  std::vector<Graph> graphs;
+  bool use_graph = true;
+  int64_t graph_replays = 0;
   // the Neumann boundary kernels (atomics path) run beside the area kernel on a second stream
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_side[2] = {};
@@ -481,6 +486,9 @@ static elres_fn elem_residual_kernel_of(int motion) {
 // what the element range [e0, e1) touches: node, equation and nnz-slot ranges (each contiguous)
 static void compute_ranges(maf_handle* h) {
   const HostModel& M = h->M;
+  for (auto& g : h->graphs)   // captured launch sequences hold the old range and order buffer
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
   const TouchedRange R = touched_range(M, h->e0, h->e1);
   h->node_lo = R.node_lo; h->node_hi = R.node_hi;
   h->eq_lo = R.eq_lo; h->eq_hi = R.eq_hi;
@@ -583,36 +591,38 @@ static void launch_atomic_range(maf_handle* h, const double* d_xms, const double
   }
 }
 
-static void do_assemble_device(maf_handle* h, const double* d_xms, const double* d_cps, double time, double dt,
-                               double bend_tm, int mode, double* d_r, double* d_nz, double* d_rn, cudaStream_t s,
-                               bool timed) {
+// timing events: while a stream is being captured into a graph they are recorded as external event nodes, so that the
+// replayed graph keeps producing the per-phase device times
+static void rec(cudaEvent_t e, cudaStream_t s, bool capturing) {
+  if (capturing) CU(cudaEventRecordWithFlags(e, s, cudaEventRecordExternal));
+  else CU(cudaEventRecord(e, s));
+}
+
+// the launches of one assembly on stream s (everything asynchronous); returns the number of kernels launched
+static int enqueue_assembly(maf_handle* h, const double* d_xms, const double* d_cps, double time, double dt,
+                            double bend_tm, int mode, double* d_r, double* d_nz, double* d_rn, cudaStream_t s,
+                            bool capturing) {
   const HostModel& M = h->M;
-  if (!d_r) d_r = h->d_r;
-  if (!d_nz) d_nz = h->d_nz;
-  if (mode != MAF_SCATTER_ATOMIC && mode != MAF_SCATTER_DETERMINISTIC) throw std::runtime_error("unknown scatter mode");
-  if (!(dt == dt) || !(time == time)) throw std::runtime_error("time / dt is NaN");
+  const int64_t launches0 = h->launches;
   area_fn kern = area_kernel_of(M.motion, mode == MAF_SCATTER_DETERMINISTIC);
   const int64_t ne = h->e1 - h->e0;
   const int grid = (int)std::min<int64_t>(std::max<int64_t>(ne, 1), (int64_t)h->grid);
-  (void)timed;
-  h->timed_valid = false;
-  CU(cudaEventRecord(h->ev[1], s));
+  rec(h->ev[1], s, capturing);
   StageSink st{nullptr, nullptr, 0};
   if (mode == MAF_SCATTER_ATOMIC) {
     // only what this element range touches (contiguous, because unknowns are numbered node-major)
     CU(cudaMemsetAsync(d_r + h->eq_lo, 0, sizeof(double) * (size_t)(h->eq_hi - h->eq_lo), s));
     CU(cudaMemsetAsync(d_nz + h->slot_lo, 0, sizeof(double) * (size_t)(h->slot_hi - h->slot_lo), s));
   } else {
-    ensure_gather(h);
-    ensure_stage(h);
     st = StageSink{h->d_kel, h->d_rel, h->nij};
   }
-  CU(cudaEventRecord(h->ev[6], s));
+  rec(h->ev[6], s, capturing);
   // atomics path: the (tiny) Neumann boundary kernels only add into r / nzval, in any order: they run on a second
   // stream beside the area kernel instead of after it
   const bool side = mode == MAF_SCATTER_ATOMIC && M.n_neu > 0 && h->side_stream;
   if (side) {
-    CU(cudaStreamWaitEvent(h->side_stream, h->ev[6], 0));
+    CU(cudaEventRecord(h->ev_side[1], s));
+    CU(cudaStreamWaitEvent(h->side_stream, h->ev_side[1], 0));
     for (int bc = 0; bc < M.n_neu; ++bc) {
       const int n = M.b_offs[bc + 1] - M.b_offs[bc];
       if (n == 0) continue;
@@ -625,15 +635,16 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
     CU(cudaEventRecord(h->ev_side[0], h->side_stream));
   }
   if (ne > 0) {
+    // (a replayed graph keeps writing the ring slot it was captured with)
     const int q = (int)(h->ring_n % MAF_RING);
-    CU(cudaEventRecord(h->ring_a[q], s));
+    rec(h->ring_a[q], s, capturing);
     kern<<<grid, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, h->d_order, h->e0, h->e1);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(h->ring_b[q], s));
+    rec(h->ring_b[q], s, capturing);
     h->ring_n += 1;
     h->launches += 1;
   }
-  CU(cudaEventRecord(h->ev[2], s));
+  rec(h->ev[2], s, capturing);
   if (mode == MAF_SCATTER_DETERMINISTIC) {
     const int gb = h->sm_count * 16;
     const int64_t p_lo = M.sym.nbr_ptr[h->node_lo], p_hi = M.sym.nbr_ptr[h->node_hi];
@@ -644,7 +655,7 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
     CU(cudaGetLastError());
     h->launches += 2;
   }
-  CU(cudaEventRecord(h->ev[3], s));
+  rec(h->ev[3], s, capturing);
   if (side) CU(cudaStreamWaitEvent(s, h->ev_side[0], 0));
   for (int bc = 0; bc < M.n_neu && !side; ++bc) {
     const int n = M.b_offs[bc + 1] - M.b_offs[bc];
@@ -664,14 +675,79 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
       }
     }
   }
-  CU(cudaEventRecord(h->ev[4], s));
-  h->timed_valid = true;
+  rec(h->ev[4], s, capturing);
   if (d_rn) {
     rnorm2_partial<<<256, 256, 0, s>>>(d_r, M.nmdf, h->d_part);
     rnorm2_final<<<1, 256, 0, s>>>(h->d_part, 256, d_rn);
     CU(cudaGetLastError());
     h->launches += 2;
   }
+  return (int)(h->launches - launches0);
+}
+
+// Small meshes (the reference's own 17 x 17 examples: ~300 elements, ~10 launches of a few microseconds each) are
+// bound by the host's launch rate, not by the device: for them the launch sequence of an assembly into the handle's
+// own buffers is captured ONCE per (scatter mode, dt, Neumann values) into a CUDA graph and replayed.
+#ifndef MAF_GRAPH_MAX_ELEMS
+#define MAF_GRAPH_MAX_ELEMS 16384
+#endif
+static void do_assemble_device(maf_handle* h, const double* d_xms, const double* d_cps, double time, double dt,
+                               double bend_tm, int mode, double* d_r, double* d_nz, double* d_rn, cudaStream_t s,
+                               bool timed) {
+  const HostModel& M = h->M;
+  if (!d_r) d_r = h->d_r;
+  if (!d_nz) d_nz = h->d_nz;
+  if (mode != MAF_SCATTER_ATOMIC && mode != MAF_SCATTER_DETERMINISTIC) throw std::runtime_error("unknown scatter mode");
+  if (!(dt == dt) || !(time == time)) throw std::runtime_error("time / dt is NaN");
+  (void)timed;
+  h->timed_valid = false;
+  if (mode == MAF_SCATTER_DETERMINISTIC) {   // allocations and uploads: never inside a capture
+    ensure_gather(h);
+    ensure_stage(h);
+  }
+  const bool graphable = h->use_graph && !h->strip && s == h->stream && d_r == h->d_r && d_nz == h->d_nz &&
+                         d_xms == h->d_xms && d_cps == h->d_cps && (d_rn == nullptr || d_rn == h->d_rn) &&
+                         M.numel <= MAF_GRAPH_MAX_ELEMS;
+  if (!graphable) {
+    enqueue_assembly(h, d_xms, d_cps, time, dt, bend_tm, mode, d_r, d_nz, d_rn, s, false);
+    h->timed_valid = true;
+    return;
+  }
+  // key: everything that is baked into the kernel arguments
+  std::vector<double> key = {(double)mode, dt, d_rn ? 1.0 : 0.0, (double)h->e0, (double)h->e1, (double)(size_t)h->d_kel};
+  for (int bc = 0; bc < M.n_neu; ++bc) key.push_back(neumann_value(M.b_type[bc], M.b_val[bc], time, bend_tm));
+  maf_handle::Graph* g = nullptr;
+  for (auto& c : h->graphs)
+    if (c.key.size() == key.size() && std::memcmp(c.key.data(), key.data(), key.size() * sizeof(double)) == 0) g = &c;
+  if (!g) {
+    if (h->graphs.size() >= 8) {   // a time-dependent Neumann value changes the key every step: keep the cache small
+      CU(cudaGraphExecDestroy(h->graphs.front().exec));
+      h->graphs.erase(h->graphs.begin());
+    }
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int n = 0;
+    try {
+      n = enqueue_assembly(h, d_xms, d_cps, time, dt, bend_tm, mode, d_r, d_nz, d_rn, s, true);
+    } catch (...) {
+      cudaStreamEndCapture(s, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    CU(cudaStreamEndCapture(s, &graph));
+    maf_handle::Graph ng;
+    ng.key = key;
+    ng.launches = n;
+    CU(cudaGraphInstantiate(&ng.exec, graph, 0));
+    CU(cudaGraphDestroy(graph));
+    h->launches -= n;   // counted per replay below
+    h->graphs.push_back(ng);
+    g = &h->graphs.back();
+  }
+  CU(cudaGraphLaunch(g->exec, s));
+  h->launches += g->launches;
+  h->graph_replays += 1;
+  h->timed_valid = true;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -869,6 +945,7 @@ static int create_handle(maf_handle** out, const maf_mesh_desc* mesh, const maf_
     if (nb < 1) throw std::runtime_error("area kernel does not fit on an SM");
     h->ctas_per_sm = nb;
     h->grid = nb * h->sm_count;  // persistent grid: a multiple of the SM count
+    if (const char* e = std::getenv("MAF_NO_GRAPH")) h->use_graph = !(*e && *e != '0');
   } catch (std::exception& e) {
     {
       std::lock_guard<std::mutex> lk(g_mu);
@@ -902,6 +979,8 @@ int maf_destroy(maf_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->lower_base && h->lower_ipc) cudaIpcCloseMemHandle(h->lower_base);
   if (h->upper_base && h->upper_ipc) cudaIpcCloseMemHandle(h->upper_base);
+  for (auto& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->strip_alloc) cudaFree(h->strip_alloc);
   if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
   for (int k = 0; k < MAF_RING; ++k) {
@@ -1275,11 +1354,12 @@ int maf_launch_count(maf_handle* h, int64_t* n) {
   MAF_API_END(h)
 }
 
-int maf_kernel_info(maf_handle* h, int64_t* out5 /* 6 values */) {
+int maf_kernel_info(maf_handle* h, int64_t* out5 /* 7 values */) {
   MAF_API_BEGIN(h)
   if (!out5) throw std::runtime_error("null output pointer");
   out5[0] = MAF_NT; out5[1] = 1; out5[2] = (int64_t)h->smem_bytes; out5[3] = h->ctas_per_sm; out5[4] = h->sm_count;
   out5[5] = h->n_slot_classes;
+  out5[6] = h->graph_replays;
   MAF_API_END(h)
 }
 

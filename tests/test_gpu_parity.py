@@ -350,3 +350,34 @@ def test_pipelined_host_path_on_a_small_mesh(monkeypatch):
     rd, nzd, _ = asm.assemble_resident(time, dt)        # and through the resident entry point
     assert np.abs(nzd - nz0).max() <= 1e-13 * np.abs(nz0).max()
     asm.close()
+
+
+def test_graph_replay_equals_plain_launches(monkeypatch):
+    """Small meshes replay their launch sequence from a CUDA graph (captured once per scatter mode / dt / Neumann
+    values): same numbers as plain launches (bitwise on the deterministic path), across changes of dt, of the element
+    range and of the time-dependent MOMENT value."""
+    name = "alevb_bend_pn_4x3"          # F_BEND: the Neumann value depends on time (FiniteElement.jl:379)
+    p, hm, om, xms, cps, time, dt, args = make_case(name)
+    monkeypatch.setenv("MAF_NO_GRAPH", "1")
+    plain = maf.Assembler(hm, p)
+    monkeypatch.delenv("MAF_NO_GRAPH")
+    graph = maf.Assembler(hm, p)
+    bt = args["bend_tm"]
+    for (t, d) in ((0.1, 0.37), (0.1, 0.37), (0.2, 0.37), (0.2, 0.5), (0.1, 0.37)):
+        for mode in (maf.SCATTER_DETERMINISTIC, maf.SCATTER_ATOMIC):
+            r0, k0, n0 = plain.assemble(xms, cps, t, d, bend_tm=bt, scatter_mode=mode)
+            r1, k1, n1 = graph.assemble(xms, cps, t, d, bend_tm=bt, scatter_mode=mode)
+            if mode == maf.SCATTER_DETERMINISTIC:
+                assert np.array_equal(r0, r1) and np.array_equal(k0, k1) and n0 == n1
+            else:
+                assert np.abs(k0 - k1).max() <= 1e-13 * np.abs(k0).max() and np.abs(r0 - r1).max() <= 1e-13 * np.abs(r0).max()
+    assert plain.kernel_info()["graph_replays"] == 0 and graph.kernel_info()["graph_replays"] == 10
+    graph.set_element_range(1, 6)
+    plain.set_element_range(1, 6)
+    r0, k0, _ = plain.assemble(xms, cps, 0.1, 0.37, bend_tm=bt, scatter_mode=maf.SCATTER_DETERMINISTIC)
+    r1, k1, _ = graph.assemble(xms, cps, 0.1, 0.37, bend_tm=bt, scatter_mode=maf.SCATTER_DETERMINISTIC)
+    i = graph.range_info()
+    sl = slice(i["slots"][0] - 1, i["slots"][1])
+    assert np.array_equal(k0[sl], k1[sl])
+    plain.close()
+    graph.close()
