@@ -248,6 +248,8 @@ def newton_gpu_times(maf, device):
             tm = asm.timings()
             dev_ms.append(tm["zero_ms"] + tm["area_ms"] + tm["bdry_ms"])
         res["kernels_device_ms"] = float(np.median(dev_ms[2:]))
+        res["kernels_device_split_ms"] = {k: tm[k] for k in ("zero_ms", "area_ms", "bdry_ms")}
+        res["graph_replays"] = asm.kernel_info()["graph_replays"]
         res["assemble_resident_call_ms"] = float(np.median(call_ms[2:]))
         res["nmdf"], res["nnz"], res["numel"] = int(mesh.nmdf), int(asm.nnz), int(mesh.numel)
         maf.pkg.host.analysis.close_assemblers(mesh)
@@ -451,6 +453,36 @@ def run(a, out_stream):
         clocks["note"] = f"timed region shorter than the sampling period: {extra} more untimed steps of the same load were sampled"
     value = mesh.numel * a.steps / (ms * 1e-3) / 1e6
 
+    # ---- the deterministic scatter path on the same workload (N = 1): bitwise reproducible, ascending element id ----
+    det = None
+    if world == 1 and a.scatter == "atomic" and not a.no_e2e:
+        dmode = maf.SCATTER_DETERMINISTIC
+        try:
+            for _ in range(2):
+                asm.assemble_device(d_x.data_ptr(), d_c.data_ptr(), dt, dt, scatter_mode=dmode, d_r=d_r.data_ptr(),
+                                    d_nzval=d_k.data_ptr(), d_rnorm2=d_n.data_ptr(), stream=None)
+            torch.cuda.synchronize()
+            nd = max(3, min(a.steps, 5))
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            for _ in range(nd):
+                asm.assemble_device(d_x.data_ptr(), d_c.data_ptr(), dt, dt, scatter_mode=dmode, d_r=d_r.data_ptr(),
+                                    d_nzval=d_k.data_ptr(), d_rnorm2=d_n.data_ptr(), stream=None)
+            d1.record()
+            torch.cuda.synchronize()
+            dms = d0.elapsed_time(d1) / nd
+            ki = asm.kernel_info()
+            det = {"value": mesh.numel / (dms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": dms,
+                   "fraction_of_atomics_rate": (mesh.numel / (dms * 1e-3) / 1e6) / value,
+                   "staging_bytes": ki["staging_bytes"], "staging_fraction_of_nzval": ki["staging_bytes"] / (asm.nnz * 8.0),
+                   "band_rows": ki["band_rows"], "rnorm2": float(d_n.item())}
+        except maf.MafError as e:
+            det = {"error": str(e)[:200]}
+        # leave the atomics result in the buffers for the checks below
+        asm.assemble_device(d_x.data_ptr(), d_c.data_ptr(), dt, dt, scatter_mode=mode, d_r=d_r.data_ptr(),
+                            d_nzval=d_k.data_ptr(), d_rnorm2=d_n.data_ptr(), stream=None)
+        torch.cuda.synchronize()
+
     # ---- e2e through the host-buffer entry point (pinned host memory) ------------------------------------------
     e2e = None
     if not a.no_e2e and world == 1:
@@ -601,7 +633,7 @@ def run(a, out_stream):
                       "device_mem_used_gb_rank0": mem_used / 1e9,
                       "setup_s": t_setup, "kernel": asm.kernel_info()},
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-           "newton_iteration": newton, "parity_spot": spot, "rnorm2": rnorm2}
+           "newton_iteration": newton, "parity_spot": spot, "value_deterministic": det, "rnorm2": rnorm2}
     out_stream.write(json.dumps(out) + "\n")
     if world > 1:
         dist.destroy_process_group()

@@ -152,8 +152,10 @@ int maf_area_kernel_times(maf_handle* h, double* out_ms, int64_t n);
  * out[2] dynamic shared memory bytes per CTA, out[3] resident CTAs per SM, out[4] SM count, out[5] number of distinct
  * element scatter maps (elements with equal maps share one: a few hundred on a structured 10^6-element patch),
  * out[6] assemblies replayed from a captured CUDA graph so far (meshes of <= 16384 elements assembling into the
- * handle's own buffers: their ~10 launches are bound by the host's launch rate; MAF_NO_GRAPH=1 disables it). */
-int maf_kernel_info(maf_handle* h, int64_t* out7);
+ * handle's own buffers: their ~10 launches are bound by the host's launch rate; MAF_NO_GRAPH=1 disables it),
+ * out[7] bytes of staging memory the deterministic path holds (0 until it ran), out[8] its band height in element
+ * rows (0 = the whole range staged at once; large ranges are staged in bands, ~6 % of nzval). */
+int maf_kernel_info(maf_handle* h, int64_t* out9);
 
 /* The static plan of the area kernel's contraction phase as text: "c,c,c/c,c/..." = the chunk ids (<= 32 tangent
  * tasks of one block each) that every warp of the CTA executes, in order. The environment variable MAF_PLAN (same

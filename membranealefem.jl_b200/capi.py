@@ -323,10 +323,10 @@ class Assembler:
         return n.value
 
     def kernel_info(self):
-        o = np.zeros(7, dtype=np.int64)
+        o = np.zeros(9, dtype=np.int64)
         self._check(self.L.maf_kernel_info(self.h, _ptr(o, C.c_int64)))
         return dict(zip(["threads_per_cta", "elements_per_cta", "smem_bytes", "ctas_per_sm", "sm_count",
-                         "scatter_map_classes", "graph_replays"], o.tolist()))
+                         "scatter_map_classes", "graph_replays", "staging_bytes", "band_rows"], o.tolist()))
 
     def chunk_plan(self):
         """Plan of the contraction phase, "c,c/c,c/..." = chunk ids per warp in execution order."""

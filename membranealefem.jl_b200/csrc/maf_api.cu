@@ -36,9 +36,10 @@ static_assert(sizeof(Config) <= 4000, "Config must fit the kernel parameter spac
 // kernels
 // ---------------------------------------------------------------------------------------------------------
 struct StageSink {      // deterministic path staging buffers (NULL = atomics path)
-  double* kel;          // numel_local x 81 x nij
-  double* rel;          // numel_local x 72
+  double* kel;          // staged elements x 81 x nij
+  double* rel;          // staged elements x 72
   int nij;
+  int64_t ring;         // 0: one block per element of [e0, e1); otherwise element e lives in block (e - e0) % ring
 };
 
 #ifdef MAF_PHASE_TIMING   // profiling build only: cycles per warp and phase, summed over all CTAs
@@ -135,7 +136,7 @@ area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __
     // (forming the residual on the warp of the IT_LIN items before this barrier was measured: -19 %, that warp
     // becomes the critical path of the Gauss phase)
 #ifndef MAF_STUB_RESIDUAL
-    phase_residual(tid, MAF_NT, cfg, fr, sm, r_gl, STAGED ? st.rel + 72 * (el - e0) : nullptr);
+    phase_residual(tid, MAF_NT, cfg, fr, sm, r_gl, STAGED ? st.rel + 72 * stage_index(el - e0, st.ring) : nullptr);
 #endif
     if (!STAGED) {
       KSink sink{nzval, nullptr, 0};
@@ -143,7 +144,7 @@ area_kernel(const __grid_constant__ Config cfg, const Tables T, const double* __
       phase_tangent<MOTION>(tid, cfg, fr, sm, sink);
 #endif
     } else {
-      KSink sink{nullptr, st.kel + (size_t)81 * st.nij * (el - e0), st.nij};
+      KSink sink{nullptr, st.kel + (size_t)81 * st.nij * stage_index(el - e0, st.ring), st.nij};
       phase_tangent<MOTION>(tid, cfg, fr, sm, sink);
     }
     async_wait_all();
@@ -414,7 +415,11 @@ struct maf_handle {
   cudaEvent_t ring_a[64] = {}, ring_b[64] = {};
   long long ring_n = 0;
   int64_t n_slot_classes = 0;         // distinct scatter maps (Tables::elslot rows)
+  size_t rk_pad = 0;                  // whole-mesh handles: d_nz = d_r + rk_pad (one allocation)
   // small meshes: the launch sequence of an assembly, captured once per key and replayed (do_assemble_device)
+  struct Band { int64_t e0, e1; int32_t* d_order; };   // deterministic path: bands of element rows (ensure_stage)
+  std::vector<Band> bands;
+  int64_t band_rows = 0, band_e0 = -1, band_e1 = -1;
   struct Graph { std::vector<double> key; cudaGraphExec_t exec = nullptr; int launches = 0; };
   std::vector<Graph> graphs;
   bool use_graph = true;
@@ -548,23 +553,78 @@ static void ensure_gather(maf_handle* h) {
   h->gather_ready = true;
 }
 
+// Staging of the deterministic path. A staged element takes (81 nij + 72) doubles, 3.4 times its share of nzval, so
+// large ranges are staged in BANDS of element rows: a band is assembled into a ring that holds two bands, then every
+// node row whose contributing element rows (n - 2 .. n) are all staged is gathered, in ascending order. The ring is
+// sized to ~6 % of the range's nzval; small ranges keep one block per element (a single band).
+#ifndef MAF_BAND_MIN_ELEMS
+#define MAF_BAND_MIN_ELEMS 65536
+#endif
 static void ensure_stage(maf_handle* h) {
+  const HostModel& M = h->M;
   const size_t ne = (size_t)(h->e1 - h->e0);
-  if (h->d_kel && h->kel_elems >= ne) return;
-  if (h->d_kel) {  // range grew: reallocate
+  const bool rows_aligned = h->e0 % M.num1el == 0 && h->e1 % M.num1el == 0;
+  int64_t band_rows = 0;   // 0: no banding
+  if ((int64_t)ne >= MAF_BAND_MIN_ELEMS && rows_aligned) {
+    const int64_t nrows = (int64_t)ne / M.num1el;
+    const double per_el = ((double)81 * h->nij + 72) * sizeof(double);
+    const double nz_bytes = (double)(h->slot_hi - h->slot_lo) * sizeof(double);
+    band_rows = std::max<int64_t>(4, (int64_t)(0.06 * nz_bytes / (2.0 * per_el * M.num1el)));
+    if (band_rows * 2 >= nrows) band_rows = 0;
+  }
+  if (band_rows) {   // the band arithmetic relies on the structured node numbering of the reference's patches
+    const int64_t num1np = M.num1el + 2;
+    bool ok = M.numnp == num1np * (M.num2el + 2);
+    for (int64_t e = h->e0; e < h->e1 && ok; ++e)
+      for (int a = 0; a < 9; ++a)
+        if (M.IX0[9 * e + a] != (e % M.num1el + a % 3) + num1np * (e / M.num1el + a / 3)) { ok = false; break; }
+    if (!ok) band_rows = 0;
+  }
+  if (const char* e = std::getenv("MAF_BAND_ROWS")) {   // tests force bands on small meshes
+    band_rows = std::atoll(e);
+    if (band_rows < 2 || !rows_aligned || band_rows * 2 >= (int64_t)ne / M.num1el) band_rows = 0;
+    const int64_t num1np = M.num1el + 2;
+    bool ok = M.numnp == num1np * (M.num2el + 2);
+    for (int64_t el = h->e0; el < h->e1 && ok; ++el)
+      for (int a = 0; a < 9; ++a)
+        if (M.IX0[9 * el + a] != (el % M.num1el + a % 3) + num1np * (el / M.num1el + a / 3)) { ok = false; break; }
+    if (!ok) band_rows = 0;
+  }
+  const size_t need_elems = band_rows ? (size_t)(2 * band_rows * M.num1el) : ne;
+  if (h->d_kel && h->kel_elems >= need_elems && h->band_rows == band_rows && h->band_e0 == h->e0 && h->band_e1 == h->e1)
+    return;
+  if (h->d_kel) {
     cudaFree(h->d_kel);
     cudaFree(h->d_rel);
     h->d_kel = h->d_rel = nullptr;
   }
+  for (auto& b : h->bands) cudaFree(b.d_order);
+  h->bands.clear();
   size_t free_b = 0, total_b = 0;
   CU(cudaMemGetInfo(&free_b, &total_b));
-  const size_t need = ne * ((size_t)81 * h->nij + 72) * sizeof(double);
+  const size_t need = need_elems * ((size_t)81 * h->nij + 72) * sizeof(double);
   if (need + ((size_t)1 << 30) > free_b)
     throw std::runtime_error("deterministic scatter needs " + std::to_string(need >> 20) +
                              " MiB of staging memory, more than is free on the device");
-  CU(cudaMalloc(&h->d_kel, ne * 81 * h->nij * sizeof(double)));
-  CU(cudaMalloc(&h->d_rel, ne * 72 * sizeof(double)));
-  h->kel_elems = ne;
+  CU(cudaMalloc(&h->d_kel, need_elems * 81 * h->nij * sizeof(double)));
+  CU(cudaMalloc(&h->d_rel, need_elems * 72 * sizeof(double)));
+  h->kel_elems = need_elems;
+  h->band_rows = band_rows;
+  h->band_e0 = h->e0;
+  h->band_e1 = h->e1;
+  if (band_rows) {
+    const int64_t r0 = h->e0 / M.num1el, r1 = h->e1 / M.num1el;
+    for (int64_t r = r0; r < r1; r += band_rows) {
+      maf_handle::Band b;
+      b.e0 = r * M.num1el;
+      b.e1 = std::min(r + band_rows, r1) * M.num1el;
+      std::vector<int32_t> order;
+      build_element_order(M.num1el, b.e0, b.e1, order);
+      CU(cudaMalloc(&b.d_order, order.size() * sizeof(int32_t)));
+      CU(cudaMemcpy(b.d_order, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      h->bands.push_back(b);
+    }
+  }
 }
 
 // area + boundary kernels of the elements [e0, e1) on the atomics path (outputs must have been zeroed)
@@ -576,7 +636,7 @@ static void launch_atomic_range(maf_handle* h, const double* d_xms, const double
   const int64_t ne = e1 - e0;
   if (ne <= 0) return;
   const int grid = (int)std::min<int64_t>(ne, (int64_t)h->grid);
-  StageSink st{nullptr, nullptr, 0};
+  StageSink st{nullptr, nullptr, 0, 0};
   kern<<<grid, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, d_order, e0, e1);
   CU(cudaGetLastError());
   h->launches += 1;
@@ -608,13 +668,18 @@ static int enqueue_assembly(maf_handle* h, const double* d_xms, const double* d_
   const int64_t ne = h->e1 - h->e0;
   const int grid = (int)std::min<int64_t>(std::max<int64_t>(ne, 1), (int64_t)h->grid);
   rec(h->ev[1], s, capturing);
-  StageSink st{nullptr, nullptr, 0};
+  StageSink st{nullptr, nullptr, 0, 0};
   if (mode == MAF_SCATTER_ATOMIC) {
     // only what this element range touches (contiguous, because unknowns are numbered node-major)
-    CU(cudaMemsetAsync(d_r + h->eq_lo, 0, sizeof(double) * (size_t)(h->eq_hi - h->eq_lo), s));
-    CU(cudaMemsetAsync(d_nz + h->slot_lo, 0, sizeof(double) * (size_t)(h->slot_hi - h->slot_lo), s));
+    if (d_r == h->d_r && d_nz == h->d_nz && !h->strip && h->eq_lo == 0 && h->eq_hi == M.nmdf && h->slot_lo == 0 &&
+        h->slot_hi == M.sym.nnz) {
+      CU(cudaMemsetAsync(d_r, 0, sizeof(double) * (h->rk_pad + (size_t)M.sym.nnz), s));
+    } else {
+      CU(cudaMemsetAsync(d_r + h->eq_lo, 0, sizeof(double) * (size_t)(h->eq_hi - h->eq_lo), s));
+      CU(cudaMemsetAsync(d_nz + h->slot_lo, 0, sizeof(double) * (size_t)(h->slot_hi - h->slot_lo), s));
+    }
   } else {
-    st = StageSink{h->d_kel, h->d_rel, h->nij};
+    st = StageSink{h->d_kel, h->d_rel, h->nij, h->band_rows ? (int64_t)h->kel_elems : 0};
   }
   rec(h->ev[6], s, capturing);
   // atomics path: the (tiny) Neumann boundary kernels only add into r / nzval, in any order: they run on a second
@@ -634,7 +699,8 @@ static int enqueue_assembly(maf_handle* h, const double* d_xms, const double* d_
     }
     CU(cudaEventRecord(h->ev_side[0], h->side_stream));
   }
-  if (ne > 0) {
+  const bool banded = mode == MAF_SCATTER_DETERMINISTIC && h->band_rows > 0;
+  if (ne > 0 && !banded) {
     // (a replayed graph keeps writing the ring slot it was captured with)
     const int q = (int)(h->ring_n % MAF_RING);
     rec(h->ring_a[q], s, capturing);
@@ -645,7 +711,7 @@ static int enqueue_assembly(maf_handle* h, const double* d_xms, const double* d_
     h->launches += 1;
   }
   rec(h->ev[2], s, capturing);
-  if (mode == MAF_SCATTER_DETERMINISTIC) {
+  if (mode == MAF_SCATTER_DETERMINISTIC && !banded) {
     const int gb = h->sm_count * 16;
     const int64_t p_lo = M.sym.nbr_ptr[h->node_lo], p_hi = M.sym.nbr_ptr[h->node_hi];
     gather_K_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, h->G, h->d_kel, h->nij, h->e0, h->e1, p_lo, p_hi, d_nz);
@@ -654,6 +720,35 @@ static int enqueue_assembly(maf_handle* h, const double* d_xms, const double* d_
                                        h->node_hi * M.ndf, d_r);
     CU(cudaGetLastError());
     h->launches += 2;
+  }
+  if (banded) {
+    // band after band: stage the band's elements (ring of two bands), then gather the node rows that are complete.
+    // Node row n of the patch takes contributions from the element rows n - 2 .. n only (quadratic splines).
+    GatherTables G = h->G;
+    G.ring = (int64_t)h->kel_elems;
+    const int64_t num1np = M.num1el + 2;          // node rows are num1el + 2 nodes long (IX of Mesh.jl:574-593)
+    int64_t node_done = h->node_lo;               // first node not gathered yet
+    const int gb = h->sm_count * 16;
+    for (size_t b = 0; b < h->bands.size(); ++b) {
+      const maf_handle::Band& B = h->bands[b];
+      const int gridb = (int)std::min<int64_t>(B.e1 - B.e0, (int64_t)h->grid);
+      // (the area kernel indexes the staging ring by el - e0 of the RANGE: pass the range start with the band's order)
+      kern<<<gridb, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, B.d_order, h->e0,
+                                              h->e0 + (B.e1 - B.e0));
+      CU(cudaGetLastError());
+      const bool last = b + 1 == h->bands.size();
+      // complete node rows: up to (first element row of the next band) - 1, i.e. all nodes below that row's first node
+      const int64_t node_hi = last ? h->node_hi : std::min<int64_t>(h->node_hi, (B.e1 / M.num1el) * num1np);
+      if (node_hi > node_done) {
+        gather_K_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, G, h->d_kel, h->nij, h->e0, h->e1, M.sym.nbr_ptr[node_done],
+                                          M.sym.nbr_ptr[node_hi], d_nz);
+        gather_r_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, G, h->d_rel, h->e0, h->e1, node_done * M.ndf, node_hi * M.ndf, d_r);
+        CU(cudaGetLastError());
+        node_done = node_hi;
+        h->launches += 2;
+      }
+      h->launches += 1;
+    }
   }
   rec(h->ev[3], s, capturing);
   if (side) CU(cudaStreamWaitEvent(s, h->ev_side[0], 0));
@@ -677,10 +772,15 @@ static int enqueue_assembly(maf_handle* h, const double* d_xms, const double* d_
   }
   rec(h->ev[4], s, capturing);
   if (d_rn) {
-    rnorm2_partial<<<256, 256, 0, s>>>(d_r, M.nmdf, h->d_part);
-    rnorm2_final<<<1, 256, 0, s>>>(h->d_part, 256, d_rn);
+    if (M.nmdf <= 32768) {   // one block sums a small system in the same fixed order every time
+      rnorm2_partial<<<1, 256, 0, s>>>(d_r, M.nmdf, d_rn);
+      h->launches += 1;
+    } else {
+      rnorm2_partial<<<256, 256, 0, s>>>(d_r, M.nmdf, h->d_part);
+      rnorm2_final<<<1, 256, 0, s>>>(h->d_part, 256, d_rn);
+      h->launches += 2;
+    }
     CU(cudaGetLastError());
-    h->launches += 2;
   }
   return (int)(h->launches - launches0);
 }
@@ -911,8 +1011,10 @@ static int create_handle(maf_handle** out, const maf_mesh_desc* mesh, const maf_
     h->d_xms = dalloc<double>(h, (size_t)3 * M.numnp);
     h->d_cps = dalloc<double>(h, (size_t)M.ndf * M.numnp);
     if (!h->strip) {
-      h->d_r = dalloc<double>(h, (size_t)M.nmdf);
-      h->d_nz = dalloc<double>(h, (size_t)M.sym.nnz);
+      // r and nzval side by side (r padded to 256 bytes): a whole-mesh assembly zeroes both with ONE memset
+      h->rk_pad = (((size_t)M.nmdf * sizeof(double) + 255) / 256) * 256 / sizeof(double);
+      h->d_r = dalloc<double>(h, h->rk_pad + (size_t)M.sym.nnz);
+      h->d_nz = h->d_r + h->rk_pad;
     } else {
       // ONE allocation (exported to the neighbours as one IPC handle): flags | r slice | nzval slice. d_r / d_nz are
       // kept as VIRTUAL bases (slice start minus the first row / slot of the slice) so that every kernel keeps
@@ -981,6 +1083,7 @@ int maf_destroy(maf_handle* h) {
   if (h->upper_base && h->upper_ipc) cudaIpcCloseMemHandle(h->upper_base);
   for (auto& g : h->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (auto& b : h->bands) cudaFree(b.d_order);
   if (h->strip_alloc) cudaFree(h->strip_alloc);
   if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
   for (int k = 0; k < MAF_RING; ++k) {
@@ -1354,12 +1457,14 @@ int maf_launch_count(maf_handle* h, int64_t* n) {
   MAF_API_END(h)
 }
 
-int maf_kernel_info(maf_handle* h, int64_t* out5 /* 7 values */) {
+int maf_kernel_info(maf_handle* h, int64_t* out5 /* 9 values */) {
   MAF_API_BEGIN(h)
   if (!out5) throw std::runtime_error("null output pointer");
   out5[0] = MAF_NT; out5[1] = 1; out5[2] = (int64_t)h->smem_bytes; out5[3] = h->ctas_per_sm; out5[4] = h->sm_count;
   out5[5] = h->n_slot_classes;
   out5[6] = h->graph_replays;
+  out5[7] = h->d_kel ? (int64_t)(h->kel_elems * ((size_t)81 * h->nij + 72) * sizeof(double)) : 0;
+  out5[8] = h->band_rows;
   MAF_API_END(h)
 }
 

@@ -19,7 +19,10 @@ struct GatherTables {
   int sym_fill;              // pattern holds rows without a class (MAF_PATTERN_SYM): they are written as zeros
   int ncls;                  // number of classes (the staging rows are padded to an even stride nij >= ncls)
   int64_t npairs;
+  int64_t ring;              // staging rows live in a ring of this many elements (bands of element rows are staged
+                             // and gathered one after the other); 0: one row block per element of the range
 };
+MAF_HD int64_t stage_index(int64_t k, int64_t ring) { return ring > 0 ? k % ring : k; }
 
 // one node pair p = (A,B): the <= 8 x 8 dof block K[(A,:),(B,:)], summed by MAF_GATHER_LANES threads.
 // A staged row (element, a, b) holds the nij (row dof, col dof) classes contiguously, ordered by (J, I) -- the order
@@ -51,7 +54,7 @@ MAF_HD void gather_K_pair(int64_t p, int s, const Config& cfg, const Tables& T, 
     for (int k = 0; k < 9; ++k)
       if (T.IX[9 * e + k] == A) a = k;
     if (a < 0) continue;
-    const double* row = kel + ((size_t)81 * (e - e0) + 9 * a + G.n2e_loc[q]) * nij;
+    const double* row = kel + ((size_t)81 * stage_index(e - e0, G.ring) + 9 * a + G.n2e_loc[q]) * nij;
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
       const int c = 2 * (s + L * k);   // a padding entry is read but never written back
@@ -104,7 +107,7 @@ MAF_HD void gather_r_row(int64_t k, const Config& cfg, const Tables& T, const Ga
   for (int64_t q = G.n2e_ptr[node]; q < G.n2e_ptr[node + 1]; ++q) {
     const int64_t e = G.n2e[q];
     if (e < e0 || e >= e1) continue;
-    s += rel[72 * (e - e0) + 9 * u + G.n2e_loc[q]];
+    s += rel[72 * stage_index(e - e0, G.ring) + 9 * u + G.n2e_loc[q]];
   }
   r_gl[eq] = s;
 }

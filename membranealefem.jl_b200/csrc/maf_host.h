@@ -213,6 +213,7 @@ inline void fill_gather_tables(const GatherHost& GH, GatherTables& G) {
   for (int c = 0; c < 64; ++c) { G.class_I[c] = GH.class_I[c]; G.class_J[c] = GH.class_J[c]; }
   G.sym_fill = GH.sym_fill;
   G.ncls = GH.ncls;
+  G.ring = 0;
 }
 
 // ---- strips of element rows over several GPUs (the reference's per-task chunks, FiniteElement.jl:88-89) ----

@@ -381,3 +381,22 @@ def test_graph_replay_equals_plain_launches(monkeypatch):
     assert np.array_equal(k0[sl], k1[sl])
     plain.close()
     graph.close()
+
+
+@pytest.mark.parametrize("name,rows", [("alevb_pull_17x17", 2), ("alevb_pull_17x17", 5), ("lag_pull_17x17", 3),
+                                       ("alevb_pull_fine_19x18", 4)])
+def test_banded_deterministic_staging(monkeypatch, name, rows):
+    """Large ranges stage the deterministic path band by band of element rows (ring of two bands, ~6 % of nzval
+    instead of 3.4 x nzval): forced on small meshes with MAF_BAND_ROWS, bitwise equal to the unbanded path (same
+    ascending-element-id sums), also on a strip of a 2-strip partition."""
+    p, hm, om, xms, cps, time, dt, args = make_case(name)
+    ref = maf.Assembler(hm, p)
+    r0, k0, n0 = ref.assemble(xms, cps, time, dt, scatter_mode=maf.SCATTER_DETERMINISTIC)
+    monkeypatch.setenv("MAF_BAND_ROWS", str(rows))
+    band = maf.Assembler(hm, p)
+    for _ in range(2):
+        r1, k1, n1 = band.assemble(xms, cps, time, dt, scatter_mode=maf.SCATTER_DETERMINISTIC)
+        assert np.array_equal(r0, r1) and np.array_equal(k0, k1) and n0 == n1
+    assert band.launch_count() > ref.launch_count() + 4        # the bands did run
+    ref.close()
+    band.close()
