@@ -41,9 +41,9 @@ inline const char* tuned_plan(int motion, int nchunks, int nwarps) {
 #endif
   // gains over the heuristic plan at 1001 x 1001 (gpurun_out/tune3_*.log of round 1; the plans are retuned whenever
   // the kernel changes -- the same plan lost 3 % when only the scatter map changed)
-  if (motion == M_ALEVB && nchunks == 14) return "1,10,12/0,9/13,11,4,6,5/2,7,8,3";                // +4.9 %
-  if (motion == M_ALEV && nchunks == 17) return "6,14,13,15,1/5,8,16/3,2,10,11/0,4,9,7,12";        // +6.5 % (+20 % over LPT)
-  if (motion == M_EUL && nchunks == 16) return "7,6,5,10/13,3,8/9,0,2,15/14,12,4,11,1";            // +5.8 %
+  if (motion == M_ALEVB && nchunks == 14) return "1,12,10/0,9/13,11,4,5,6/2,7,8,3";                // +4.9 % (r2 retune: +0.6 %)
+  if (motion == M_ALEV && nchunks == 17) return "6,14,13,15,1/8,5,16/3,2,10,11/0,4,9,7,12";        // +6.5 % (+20 % over LPT)
+  if (motion == M_EUL && nchunks == 16) return "6,7,5,10/13,3,8/9,0,2,15/14,12,4,11,1";            // +5.8 % (r2 retune: +0.9 %)
   if (motion == M_LAG && nchunks == 6) return "1/2/0,4/3,5";                                       // +0.6 %
   return nullptr;
 }
