@@ -23,4 +23,28 @@ for motion, n in ((maf.ALEVB, 19), (maf.LAG, 9), (maf.EUL, 7), (maf.ALEV, 7), (m
         adj, maps = maf.get_adj_maps(mesh.num1el, mesh.numel, mesh.IX, p.poly)
         asm.elem_v_residuals(adj)
     asm.close()
+    # round 2: strips behind the C ABI (flag kernels, peer pull-add, sliced tables), banded deterministic staging
+    if n >= 7:
+        strips = [maf.Assembler(mesh, p, strip=(k, 2)) for k in range(2)]
+        strips[0].peer_attach_local(None, strips[1])
+        strips[1].peer_attach_local(strips[0], None)
+        for mode in (maf.SCATTER_ATOMIC, maf.SCATTER_DETERMINISTIC):
+            for s_ in strips:
+                s_.state_set(xms, cps)
+            for s_ in strips:
+                s_.assemble_strip(None, None, 0.5, 0.5, scatter_mode=mode)
+            for s_ in strips:
+                s_.sync()
+        own = [s_.strip_info()["own_slots"] for s_ in strips]
+        nz2 = np.concatenate([s_.download(1, 0, o[0], o[1] - o[0] + 1)[1] for s_, o in zip(strips, own)])
+        assert np.abs(nz2 - nz).max() <= 1e-12 * np.abs(nz).max()
+        for s_ in strips:
+            s_.close()
+        os.environ["MAF_BAND_ROWS"] = "2"
+        os.environ["MAF_NO_GRAPH"] = "1"
+        band = maf.Assembler(mesh, p)
+        rb, nzb, _ = band.assemble(xms, cps, 0.5, 0.5, scatter_mode=maf.SCATTER_DETERMINISTIC)
+        assert np.array_equal(nzb, nz)
+        band.close()
+        del os.environ["MAF_BAND_ROWS"], os.environ["MAF_NO_GRAPH"]
     print("ok", int(motion), n, float(rn))
