@@ -218,6 +218,7 @@ def newton_gpu_times(maf, device):
                 cps[node - 1, mesh.dofs[U.vx] - 1] = 0.2
                 cps[node - 1, mesh.dofs[U.vmx] - 1] = 0.2
         res = {}
+        maf.calc_r_K(mesh, xms, cps, 0.5, 0.5, p, device=device)     # warm-up: handle creation, first launches
         for label, kw in (("host_buffers+scratch_lu", {}), ("resident+pattern_solver", {"resident": True, "solver": "pattern"})):
             x, c = xms.copy(), cps.copy()
             timers = {}

@@ -239,6 +239,27 @@ boundary_kernel(const __grid_constant__ Config cfg, const Tables T, const Bounda
   }
 }
 
+// Small meshes: one CTA per (Neumann condition, boundary element) in ONE launch. With a few dozen boundary elements
+// the warp-per-element kernel above is a chain of ~25 us per launch (729 tangent entries per warp) -- longer than
+// the area kernel of a 17 x 17 mesh; 128 threads per element cut it to a quarter.
+struct NeumannValues { double fval[8]; };
+__global__ void __launch_bounds__(128)
+boundary_kernel_cta(const __grid_constant__ Config cfg, const Tables T, const BoundaryTables BT, const NeumannValues nv,
+                    double dt, const double* __restrict__ xms, double* __restrict__ r_gl, double* __restrict__ nzval,
+                    int64_t e0, int64_t e1) {
+  __shared__ double sm[B_DOUBLES];
+  const int bc = blockIdx.y;
+  const int n = BT.offs[bc + 1] - BT.offs[bc];
+  if ((int)blockIdx.x >= n) return;
+  const int64_t el = BT.elems[BT.offs[bc] + blockIdx.x];
+  if (el < e0 || el >= e1) return;
+  boundary_gather(threadIdx.x, 128, cfg, T, BT, bc, el, xms, sm);
+  __syncthreads();
+  boundary_gauss(threadIdx.x, 128, cfg, BT, bc, nv.fval[bc], dt, sm);
+  __syncthreads();
+  boundary_scatter(threadIdx.x, 128, cfg, T, sm, r_gl, nzval, false);
+}
+
 // Deterministic path (maf_gather.cuh): MAF_GATHER_LANES threads per node pair, one thread per residual row.
 __global__ void __launch_bounds__(128)
 gather_K_kernel(const __grid_constant__ Config cfg, const Tables T, const GatherTables G,
@@ -688,14 +709,26 @@ static int enqueue_assembly(maf_handle* h, const double* d_xms, const double* d_
   if (side) {
     CU(cudaEventRecord(h->ev_side[1], s));
     CU(cudaStreamWaitEvent(h->side_stream, h->ev_side[1], 0));
-    for (int bc = 0; bc < M.n_neu; ++bc) {
-      const int n = M.b_offs[bc + 1] - M.b_offs[bc];
-      if (n == 0) continue;
-      const double fval = neumann_value(M.b_type[bc], M.b_val[bc], time, bend_tm);
-      const int gb = std::min((n + 3) / 4, h->sm_count * 8);
-      boundary_kernel<<<gb, 128, 0, h->side_stream>>>(M.cfg, h->T, h->BT, bc, fval, dt, d_xms, d_r, d_nz, -1, 1, h->e0, h->e1);
+    int nmax = 0;
+    for (int bc = 0; bc < M.n_neu; ++bc) nmax = std::max(nmax, M.b_offs[bc + 1] - M.b_offs[bc]);
+    if (M.n_neu <= 8 && nmax > 0 && (int64_t)nmax * M.n_neu <= 2048) {   // few boundary elements: a CTA each, one launch
+      NeumannValues nv;
+      for (int bc = 0; bc < 8; ++bc)
+        nv.fval[bc] = bc < M.n_neu ? neumann_value(M.b_type[bc], M.b_val[bc], time, bend_tm) : 0.0;
+      boundary_kernel_cta<<<dim3((unsigned)nmax, (unsigned)M.n_neu), 128, 0, h->side_stream>>>(
+          M.cfg, h->T, h->BT, nv, dt, d_xms, d_r, d_nz, h->e0, h->e1);
       CU(cudaGetLastError());
       h->launches += 1;
+    } else {
+      for (int bc = 0; bc < M.n_neu; ++bc) {
+        const int n = M.b_offs[bc + 1] - M.b_offs[bc];
+        if (n == 0) continue;
+        const double fval = neumann_value(M.b_type[bc], M.b_val[bc], time, bend_tm);
+        const int gb = std::min((n + 3) / 4, h->sm_count * 8);
+        boundary_kernel<<<gb, 128, 0, h->side_stream>>>(M.cfg, h->T, h->BT, bc, fval, dt, d_xms, d_r, d_nz, -1, 1, h->e0, h->e1);
+        CU(cudaGetLastError());
+        h->launches += 1;
+      }
     }
     CU(cudaEventRecord(h->ev_side[0], h->side_stream));
   }
