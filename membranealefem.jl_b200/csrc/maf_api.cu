@@ -376,9 +376,13 @@ __global__ void flag_kernel(volatile long long* signal, long long sval, volatile
     __threadfence_system();
   }
 }
-__global__ void __launch_bounds__(256) pull_add_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t n) {
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
-    dst[k] += __ldcv(src + k);
+__global__ void __launch_bounds__(256)
+pull_add_kernel(double* __restrict__ dst_r, const double* __restrict__ src_r, int64_t nr, double* __restrict__ dst_k,
+                const double* __restrict__ src_k, int64_t nk) {   // rows of r, then entries of nzval, one launch
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nr + nk; k += (int64_t)gridDim.x * blockDim.x) {
+    if (k < nr) dst_r[k] += __ldcv(src_r + k);
+    else dst_k[k - nr] += __ldcv(src_k + (k - nr));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1634,10 +1638,11 @@ static void assemble_strip(maf_handle* h, const double* d_xms, const double* d_c
     const int64_t nr = L.eq_hi - h->eq_lo, nk = L.slot_hi - h->slot_lo;
     const double* lr = reinterpret_cast<const double*>((const char*)h->lower_base + strip_r_offset()) + (h->eq_lo - L.eq_lo);
     const double* lk = reinterpret_cast<const double*>((const char*)h->lower_base + strip_nz_offset(L)) + (h->slot_lo - L.slot_lo);
-    if (nr > 0) pull_add_kernel<<<(unsigned)std::min<int64_t>((nr + 255) / 256, h->sm_count * 4), 256, 0, s>>>(h->d_r + h->eq_lo, lr, nr);
-    if (nk > 0) pull_add_kernel<<<(unsigned)std::min<int64_t>((nk + 255) / 256, h->sm_count * 8), 256, 0, s>>>(h->d_nz + h->slot_lo, lk, nk);
+    if (nr + nk > 0)
+      pull_add_kernel<<<(unsigned)std::min<int64_t>((nr + nk + 255) / 256, h->sm_count * 8), 256, 0, s>>>(
+          h->d_r + h->eq_lo, lr, std::max<int64_t>(nr, 0), h->d_nz + h->slot_lo, lk, std::max<int64_t>(nk, 0));
     CU(cudaGetLastError());
-    h->launches += 2;
+    h->launches += 1;
     // 5. the lower strip may reuse its buffer
     flag_kernel<<<1, 1, 0, s>>>(lower_flags + 1, step, nullptr, 0, err, spins);
     h->launches += 1;
