@@ -586,10 +586,10 @@ def run(a, out_stream):
     ach_tf = my_elems * F_EL[a.motion] / (area * 1e-3) / 1e12
     # DRAM bytes of one launch of this kernel on this workload, from the committed `ncu --set full` capture
     traffic, traffic_src = None, None
-    tfile = os.path.join(ROOT, "profiles", "r1_area_kernel_alevb_1001_traffic.json")
+    tfile = os.path.join(ROOT, "profiles", "r2_area_kernel_alevb_1001_traffic.json")
     if a.motion == "ALEVB" and a.n == 1001 and a.scatter == "atomic" and world == 1 and os.path.exists(tfile):
         tj = json.load(open(tfile))
-        traffic, traffic_src = tj["dram_read"] + tj["dram_write"], "profiles/r1_area_kernel_alevb_1001_full.txt"
+        traffic, traffic_src = tj["dram_read"] + tj["dram_write"], "profiles/r2_area_kernel_alevb_1001_full.txt"
     roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                 "traffic": traffic, "traffic_source": traffic_src, "kernel": f"area_kernel<{a.motion}>", "kernel_ms": area,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",

@@ -1,5 +1,5 @@
 """Attribute the per-SASS-instruction samples of an ncu source-page CSV to the phases of the area kernel (line ranges of
-maf_element.cuh at the end of round 1). usage: ncu_by_phase.py <sass csv> <nvdisasm -g -c listing of the kernel> <numel>"""
+maf_element.cuh, located by their function names). usage: ncu_by_phase.py <sass csv> <nvdisasm -g -c listing of the kernel> <numel>"""
 import csv, re, sys, collections
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
@@ -10,8 +10,21 @@ for l in open(sys.argv[2]):
     if m: cur = (m.group(1).split("/")[-1], int(m.group(2))); continue
     if re.match(r"\s+/\*[0-9a-f]{4,5}\*/", l): lines.append(cur)
 numel = float(sys.argv[3])
-R = [("gather", 240, 388), ("interp", 389, 429), ("gauss_item", 430, 662), ("residual", 663, 714), ("blk_short", 715, 772), ("blk_tr", 773, 820),
-     ("blk_mesh", 821, 883), ("blk_fused", 884, 960), ("scatter", 961, 1017), ("task_setup", 1018, 1067), ("phase_tangent", 1068, 1120)]
+# phase = the line range between two markers of maf_element.cuh (found by text, so that edits do not shift them)
+MARK = [("gather", "MAF_HD void build_basis_block"), ("interp", "MAF_HD void phase_interp"),
+        ("gauss_item", "MAF_HD int a_index"), ("residual", "MAF_HD void phase_residual"),
+        ("blk_short", "MAF_HD int ch_fo"), ("blk_tr", "MAF_HD void block_accumulate_tr"),
+        ("blk_mesh", "MAF_HD void block_accumulate_mesh"), ("blk_fused", "MAF_HD void block_accumulate_fused"),
+        ("scatter", "struct KSink"), ("task_setup", "template <int MOTION> struct SmallUnroll"),
+        ("phase_tangent", "MAF_HD void phase_tangent(")]
+import os
+src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "membranealefem.jl_b200", "csrc",
+                        "maf_element.cuh")).read().splitlines()
+starts = []
+for name, text in MARK:
+    ln = next(i + 1 for i, l in enumerate(src) if text in l)
+    starts.append((name, ln - (1 if name in ("blk_tr", "blk_mesh") else 0)))
+R = [(n, lo, (starts[i + 1][1] - 1) if i + 1 < len(starts) else len(src)) for i, (n, lo) in enumerate(starts)]
 def rng(f, ln):
     if f != "maf_element.cuh": return None
     for n, lo, hi in R:
