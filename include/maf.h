@@ -241,6 +241,11 @@ int maf_assemble_resident(maf_handle* h, double time, double dt, double bend_tm,
  * (Analysis.jl:48). */
 int maf_elem_v_residuals(maf_handle* h, const int64_t* el_ids, int64_t n, double* rv);
 
+/* generate_output (src/Output.jl:32-118) on the resident state: positions and unknowns at every area Gauss point,
+ * boundary Gauss point and corner of the patch. xout: (3 num1el + 2) x (3 num2el + 2) x 3, uout: ... x ndf, column-major
+ * like the reference's arrays. Needs the structured patch numbering of Mesh.jl:574-593. */
+int maf_generate_output(maf_handle* h, double* xout, double* uout);
+
 /* Page-lock / release a host buffer the caller owns (cudaHostRegister): maf_assemble copies from and into
  * page-locked memory directly and at the full PCIe rate (pageable buffers work too, through staging copies). The
  * outputs of calc_r_K have a fixed size per mesh (FiniteElement.jl:75-200 allocates them anew every call), so a host

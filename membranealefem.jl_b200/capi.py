@@ -48,7 +48,7 @@ EXPORTS = ["maf_create", "maf_destroy", "maf_last_error", "maf_nnz", "maf_patter
            "maf_assemble_resident", "maf_elem_v_residuals", "maf_host_register", "maf_host_unregister",
            "maf_colptr", "maf_pattern_columns", "maf_download", "maf_create_strip", "maf_strip_info",
            "maf_peer_attach_local", "maf_peer_export", "maf_peer_attach", "maf_assemble_strip",
-           "maf_assemble_strip_host", "maf_strip_timings", "maf_area_kernel_times"]
+           "maf_assemble_strip_host", "maf_strip_timings", "maf_area_kernel_times", "maf_generate_output"]
 
 
 def load_library(path=None):
@@ -77,6 +77,7 @@ def load_library(path=None):
     L.maf_assemble_strip_host.argtypes = [C.c_void_p, _F64P, _F64P, C.c_double, C.c_double, C.c_double, C.c_int,
                                           _F64P, _F64P, _F64P]
     L.maf_strip_timings.argtypes = [C.c_void_p, _F64P]
+    L.maf_generate_output.argtypes = [C.c_void_p, _F64P, _F64P]
     L.maf_colptr.argtypes = [C.c_void_p, _I64P]
     L.maf_pattern_columns.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _I64P]
     L.maf_download.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _F64P, C.c_int64, C.c_int64, _F64P]
@@ -279,6 +280,14 @@ class Assembler:
         self._check(self.L.maf_assemble_resident(self.h, time, dt, bend_tm, scatter_mode, _ptr(r, C.c_double),
                                                  _ptr(nzval, C.c_double), C.byref(rn)))
         return r, nzval, rn.value
+
+    def generate_output(self):
+        """generate_output (Output.jl:32-118) of the resident state: (xout[n1, n2, 3], uout[n1, n2, ndf])."""
+        n1, n2 = 3 * self.mesh.num1el + 2, 3 * self.mesh.num2el + 2
+        xout = np.empty((n1, n2, 3), order="F")
+        uout = np.empty((n1, n2, self.mesh.ndf), order="F")
+        self._check(self.L.maf_generate_output(self.h, _ptr(xout, C.c_double), _ptr(uout, C.c_double)))
+        return xout, uout
 
     def elem_v_residuals(self, el_ids):
         """rv of calc_elem_dof_residuals for the listed elements (1-based) on the resident state: (n, 27)."""

@@ -328,6 +328,37 @@ __global__ void state_predict_kernel(const __grid_constant__ Config cfg, const T
     state_predict_entry(k, cfg, T, dt, xms, cps);
 }
 
+// generate_output (Output.jl:32-118): positions and unknowns sampled at every area Gauss point, boundary Gauss point
+// and corner of the patch -- a tensor-product grid of (3 num1el + 2) x (3 num2el + 2) points whose 1-D basis values
+// are the line tables (interior points) and the edge tables (first / last point of a direction). One thread per
+// (point, output column); output arrays column-major like the reference's xout[n1, n2, XDIM], uout[n1, n2, ndf].
+__global__ void __launch_bounds__(256)
+sample_output_kernel(const Tables T, const BoundaryTables BT, int ndf, int num2el, const double* __restrict__ xms,
+                     const double* __restrict__ cps, double* __restrict__ xout, double* __restrict__ uout) {
+  const int64_t n1 = 3 * (int64_t)T.num1el + 2, n2 = 3 * (int64_t)num2el + 2, npt = n1 * n2;
+  const int64_t total = npt * (3 + ndf);
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pt = k % npt;
+    const int col = (int)(k / npt);
+    const int64_t s1 = pt % n1, s2 = pt / n1;
+    int e1, e2;
+    const double *f1, *f2;
+    if (s1 == 0) { e1 = 0; f1 = BT.edge1; }
+    else if (s1 == n1 - 1) { e1 = T.num1el - 1; f1 = BT.edge1 + 10; }
+    else { e1 = (int)((s1 - 1) / 3); f1 = T.line1 + 30 * T.uel1[e1] + 10 * ((s1 - 1) % 3); }
+    if (s2 == 0) { e2 = 0; f2 = BT.edge2; }
+    else if (s2 == n2 - 1) { e2 = num2el - 1; f2 = BT.edge2 + 10; }
+    else { e2 = (int)((s2 - 1) / 3); f2 = T.line2 + 30 * T.uel2[e2] + 10 * ((s2 - 1) % 3); }
+    const int32_t* ix = T.IX + 9 * ((int64_t)e1 + (int64_t)T.num1el * e2);
+    const double* src = col < 3 ? xms + T.numnp * col : cps + T.numnp * (col - 3);
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) acc += src[ix[a]] * (f1[1 + a % 3] * f2[1 + a / 3]);   // N[a] = N1[a1] N2[a2]
+    if (col < 3) xout[pt + npt * col] = acc;
+    else uout[pt + npt * (col - 3)] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(256) rnorm2_partial(const double* __restrict__ r, int64_t n, double* part) {
   __shared__ double s[256];
   double acc = 0.0;
@@ -1356,6 +1387,39 @@ int maf_assemble_resident(maf_handle* h, double time, double dt, double bend_tm,
   if (h->strip) throw std::runtime_error("strip handle: use maf_assemble_strip / maf_assemble_strip_host");
   CU(cudaEventRecord(h->ev[0], h->stream));
   assemble_to_host(h, time, dt, bend_tm, scatter_mode, r, nzval, rnorm2);
+  MAF_API_END(h)
+}
+
+int maf_generate_output(maf_handle* h, double* xout, double* uout) {
+  MAF_API_BEGIN(h)
+  require_state(h);
+  if (!xout || !uout) throw std::runtime_error("null buffer");
+  if (h->strip) throw std::runtime_error("generate_output needs a whole-mesh handle");
+  const HostModel& M = h->M;
+  {   // the sampling grid is the reference's structured patch (IX of Mesh.jl:574-593)
+    const int64_t num1np = M.num1el + 2;
+    bool ok = M.numnp == num1np * (M.num2el + 2);
+    for (int64_t e = 0; e < M.numel && ok; ++e)
+      for (int a = 0; a < 9; ++a)
+        if (M.IX0[9 * e + a] != (e % M.num1el + a % 3) + num1np * (e / M.num1el + a / 3)) { ok = false; break; }
+    if (!ok) throw std::runtime_error("generate_output needs the structured patch numbering of Mesh.jl:574-593");
+  }
+  const int64_t npt = (3 * (int64_t)M.num1el + 2) * (3 * (int64_t)M.num2el + 2);
+  double *dx = nullptr, *du = nullptr;
+  CU(cudaMalloc(&dx, sizeof(double) * (size_t)npt * 3));
+  cudaError_t err = cudaMalloc(&du, sizeof(double) * (size_t)npt * M.ndf);
+  if (err == cudaSuccess) {
+    const int grid = (int)std::min<int64_t>((npt * (3 + M.ndf) + 255) / 256, (int64_t)h->sm_count * 32);
+    sample_output_kernel<<<grid, 256, 0, h->stream>>>(h->T, h->BT, M.ndf, M.num2el, h->d_xms, h->d_cps, dx, du);
+    h->launches += 1;
+    err = cudaGetLastError();
+  }
+  if (err == cudaSuccess) err = cudaMemcpyAsync(xout, dx, sizeof(double) * (size_t)npt * 3, cudaMemcpyDeviceToHost, h->stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(uout, du, sizeof(double) * (size_t)npt * M.ndf, cudaMemcpyDeviceToHost, h->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
+  cudaFree(dx);
+  if (du) cudaFree(du);
+  CU(err);
   MAF_API_END(h)
 }
 

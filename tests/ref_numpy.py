@@ -155,3 +155,43 @@ def elem_r_K(resfn, xe, ce, active, mmo, dt, ndf, h=1e-30):
                 col = col + dt * resfn(x2, ce).imag / h
             K[:, d + ndf * a] = col
     return r, K
+
+
+def generate_output_ref(mesh, xms, cps):
+    """Output.jl:32-118, statement by statement (area Gauss points :41-54, boundary Gauss points :57-88, corners
+    :91-115), on the host mirror's mesh accessors. Test-side restatement for maf_generate_output."""
+    import mafb200 as maf
+    GP1D = 3
+    n1, n2 = mesh.num1el * GP1D + 2, mesh.num2el * GP1D + 2
+    xout = np.zeros((n1, n2, 3))
+    uout = np.zeros((n1, n2, mesh.ndf))
+    for el2 in range(1, mesh.num2el + 1):
+        for el1 in range(1, mesh.num1el + 1):
+            el = el1 + mesh.num1el * (el2 - 1)
+            nodes = mesh.IX[:, el - 1] - 1
+            for gp2 in range(1, GP1D + 1):
+                for gp1 in range(1, GP1D + 1):
+                    N = maf.get_N(el, gp1 + GP1D * (gp2 - 1), mesh)
+                    o1, o2 = (el1 - 1) * GP1D + gp1, (el2 - 1) * GP1D + gp2          # 0-based of out_id = ... + 1
+                    xout[o1, o2, :] = xms[nodes, :].T @ N
+                    uout[o1, o2, :] = cps[nodes, :].T @ N
+    for bdry in (maf.BOTTOM, maf.RIGHT, maf.TOP, maf.LEFT):
+        out_id = 2
+        for el in mesh.bdry_elems[bdry]:
+            nodes = mesh.IX[:, el - 1] - 1
+            for gp in range(1, GP1D + 1):
+                N = maf.get_N(bdry, int(el), gp, mesh)
+                o1, o2 = {maf.BOTTOM: (out_id, 1), maf.RIGHT: (n1, out_id), maf.TOP: (out_id, n2),
+                          maf.LEFT: (1, out_id)}[bdry]
+                xout[o1 - 1, o2 - 1, :] = xms[nodes, :].T @ N
+                uout[o1 - 1, o2 - 1, :] = cps[nodes, :].T @ N
+                out_id += 1
+    l1, l2 = mesh.line_gp_fns1, mesh.line_gp_fns2
+    corners = {(1, 1): (1, l1.edge[0], l2.edge[0]), (n1, 1): (mesh.num1el, l1.edge[1], l2.edge[0]),
+               (1, n2): (mesh.numel - mesh.num1el + 1, l1.edge[0], l2.edge[1]), (n1, n2): (mesh.numel, l1.edge[1], l2.edge[1])}
+    for (o1, o2), (el, f1, f2) in corners.items():                                   # crnr_gp_fns, Mesh.jl:228-233
+        nodes = mesh.IX[:, el - 1] - 1
+        N = np.array([f1[1 + a % 3] * f2[1 + a // 3] for a in range(9)])
+        xout[o1 - 1, o2 - 1, :] = xms[nodes, :].T @ N
+        uout[o1 - 1, o2 - 1, :] = cps[nodes, :].T @ N
+    return xout, uout

@@ -134,3 +134,22 @@ def test_gpu_pull_force_matches_oracle(name):
     with pytest.raises(maf.MafError, match="outside 1..numel"):
         asm.elem_v_residuals([0])
     asm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["alevb_pull_fine_19x18", "lag_bend_4x3", "static_pois_5x3"])
+def test_generate_output_on_the_device(name):
+    """maf_generate_output (Output.jl:32-118): positions and unknowns at every area / boundary Gauss
+    point and corner, against the statement-by-statement numpy restatement on the host mirror's tables."""
+    from cases import make_case
+    from ref_numpy import generate_output_ref
+    p, hm, om, xms, cps, time, dt, args = make_case(name)
+    asm = maf.Assembler(hm, p)
+    asm.state_set(xms, cps)
+    xo, uo = asm.generate_output()
+    xr, ur = generate_output_ref(hm, xms, cps)
+    assert xo.shape == xr.shape and uo.shape == ur.shape
+    assert np.abs(xo - xr).max() <= 1e-14 * np.abs(xr).max() and np.abs(uo - ur).max() <= 1e-14 * max(np.abs(ur).max(), 1.0)
+    # the corners of the flat-in-parameter patch are interpolated exactly by the clamped splines
+    assert np.allclose(xo[0, 0, :2], xms[0, :2]) and np.allclose(xo[-1, -1, :2], xms[-1, :2])
+    asm.close()
