@@ -537,6 +537,33 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const 
 #pragma unroll
       for (int i = 0; i < 3; ++i) ad[al][i] = Dual(a[al][i], (al == it.gamma && i == it.j) ? dt : 0.0);
     GpStress<Dual> S;
+#ifdef MAF_GEO_A_CLOSED_GEOM   // variant: metric tangent in closed form instead of dual numbers through gp_geom --
+                               // 48 FP64 instructions fewer per item, same results, measured 2 % (LAG 4 %) SLOWER
+                               // (profiles/r2_variants.md); kept for the record, off by default
+    GpGeom<double> g0;
+    gp_geom(a, g0);
+    GpGeom<Dual> gd;
+    gp_geom_tangent(g0, it.gamma, it.j, dt, gd);
+    if (MOTION == M_LAG) {  // mesh velocity = v
+      Dual dvd[2][3];
+#pragma unroll
+      for (int al = 0; al < 2; ++al)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) dvd[al][i] = Dual(dv[al][i], (al == it.gamma && i == it.j) ? 1.0 : 0.0);
+      Dual vd[3] = {Dual(v[0]), Dual(v[1]), Dual(v[2])};
+      gp_eval_geom<MOTION, Dual, double, Dual, double, double>(gd, ad, c, dvd, vd, dm, vm, lam, pm, cfg.mat, S);
+    } else {               // mesh velocity = vm
+      Dual dmd[2][3];
+#pragma unroll
+      for (int al = 0; al < 2; ++al)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) dmd[al][i] = Dual(dm[al][i], (al == it.gamma && i == it.j) ? 1.0 : 0.0);
+      Dual vmd[3] = {Dual(vm[0]), Dual(vm[1]), Dual(vm[2])};
+      gp_eval_geom<MOTION, Dual, double, double, Dual, double>(gd, ad, c, dv, v, dmd, vmd, lam, pm, cfg.mat, S);
+    }
+    store_column(cfg, Agp, w, S, mf, it.j, CH_N1 + it.gamma);
+    return;
+#endif
     if (MOTION == M_LAG) {  // mesh velocity = v
       Dual dvd[2][3];
 #pragma unroll

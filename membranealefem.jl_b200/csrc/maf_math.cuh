@@ -230,7 +230,54 @@ MAF_HD void gp_core(const GpGeom<TA>& g, const TA a[2][3], const TB b[3], const 
   }
 }
 
-// Full evaluation from the interpolated fields: c[k][i] = x_{,11} x_{,22} x_{,12} (GeoDynStress.jl:115).
+// Tangent of the metric quantities in the direction  d a_gamma = dt e_j  (one Cartesian component of one tangent
+// vector), in closed form from the primal ones -- what gp_geom<Dual> would produce, without its dual division and
+// square root (a third of the FP64 work of a GEO_A item and its two longest dependent chains):
+//   d det = 2 det dt a^gamma_j            d J = J dt a^gamma_j            d (1/J) = -(1/J) dt a^gamma_j
+//   d a^{al be} = -dt (a^{al gamma} a^be_j + a^al_j a^{gamma be})
+//   d n_i = -dt a^gamma_i n_j             d a^mu_i = dt (a^{mu gamma} n_i n_j - a^mu_j a^gamma_i)
+MAF_HD void gp_geom_tangent(const GpGeom<double>& g, int gamma, int j, double dt, GpGeom<Dual>& gd) {
+  // (gamma, j) are per-lane run-time values: selected with conditionals, never by indexing (an array indexed at run
+  // time would be placed in local memory)
+  const double A0g = gamma == 0 ? g.A11 : g.A12, A1g = gamma == 0 ? g.A12 : g.A22;   // a^{mu gamma}
+  const double ug[3] = {gamma == 0 ? g.up[0][0] : g.up[1][0], gamma == 0 ? g.up[0][1] : g.up[1][1],
+                        gamma == 0 ? g.up[0][2] : g.up[1][2]};                       // a^gamma_i
+  const double u0 = dt * (j == 0 ? g.up[0][0] : (j == 1 ? g.up[0][1] : g.up[0][2]));   // dt a^1_j
+  const double u1 = dt * (j == 0 ? g.up[1][0] : (j == 1 ? g.up[1][1] : g.up[1][2]));   // dt a^2_j
+  const double nj = dt * (j == 0 ? g.n[0] : (j == 1 ? g.n[1] : g.n[2]));
+  const double u = gamma == 0 ? u0 : u1;                                               // dt a^gamma_j
+  gd.J = Dual(g.J, g.J * u);
+  gd.iJ = Dual(g.iJ, -(g.iJ * u));
+  gd.idet = Dual(g.idet, -2.0 * (g.idet * u));
+  gd.A11 = Dual(g.A11, -2.0 * (A0g * u0));
+  gd.A22 = Dual(g.A22, -2.0 * (A1g * u1));
+  gd.A12 = Dual(g.A12, -(A0g * u1 + u0 * A1g));
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    gd.n[i] = Dual(g.n[i], -(ug[i] * nj));
+    const double nn = g.n[i] * nj;
+    gd.up[0][i] = Dual(g.up[0][i], A0g * nn - u0 * ug[i]);
+    gd.up[1][i] = Dual(g.up[1][i], A1g * nn - u1 * ug[i]);
+  }
+}
+
+// Full evaluation from the interpolated fields: c[k][i] = x_{,11} x_{,22} x_{,12} (GeoDynStress.jl:115); the metric
+// quantities g belong to a (gp_geom, or gp_geom_tangent for a seeded direction).
+template <int MOTION, class TA, class TC, class TV, class TM, class TS>
+MAF_HD void gp_eval_geom(const GpGeom<TA>& g, const TA a[2][3], const TC c[3][3], const TV dv[2][3], const TV v[3],
+                         const TM dm[2][3], const TM vm[3], TS lam, TS pm, const Material& mat,
+                         GpStress<typename Prom<typename Prom<typename Prom<TA, TC>::T, typename Prom<TV, TM>::T>::T, TS>::T>& out) {
+  typedef typename Prom<TA, TC>::T TG;
+  TG b[3], Gam[3][2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    b[k] = c[k][0] * g.n[0] + c[k][1] * g.n[1] + c[k][2] * g.n[2];
+#pragma unroll
+    for (int mu = 0; mu < 2; ++mu) Gam[k][mu] = c[k][0] * g.up[mu][0] + c[k][1] * g.up[mu][1] + c[k][2] * g.up[mu][2];
+  }
+  gp_core<MOTION>(g, a, b, Gam, dv, v, dm, vm, lam, pm, mat, out);
+}
+
 template <int MOTION, class TA, class TC, class TV, class TM, class TS>
 MAF_HD void gp_eval(const TA a[2][3], const TC c[3][3], const TV dv[2][3], const TV v[3], const TM dm[2][3],
                     const TM vm[3], TS lam, TS pm, const Material& mat,
