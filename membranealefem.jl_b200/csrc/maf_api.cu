@@ -446,10 +446,15 @@ struct maf_handle {
   bool timed_valid = false;
   // pipelined host path (maf_assemble): strips of element rows whose finished nzval/r ranges are copied to the
   // host on a second stream while the next strip is being assembled
-  struct Strip { int64_t e0, e1, eq_lo, slot_lo; int32_t* d_order; };
+  // (sub-)strips of element rows of the handle's range: the atomics path of a large range assembles them one after
+  // the other, so that the zero-fill of the next ones (second stream) and the device-to-host copy of the finished
+  // ones (maf_assemble, copy stream) overlap the kernels
+  struct Strip { int64_t e0, e1, eq_lo, slot_lo, eq_hi, slot_hi; int32_t* d_order; };
   std::vector<Strip> strips;
+  int64_t strips_e0 = -1, strips_e1 = -1;
   cudaStream_t copy_stream = nullptr;
-  std::vector<cudaEvent_t> strip_ev;
+  std::vector<cudaEvent_t> strip_ev, zero_ev;
+  bool host_copy_follows = false;   // set by maf_assemble around its device part: sub-strips pay only then
   int64_t launches = 0;
   float ms[7] = {0, 0, 0, 0, 0, 0, 0};
   // ---- strip mode (maf_create_strip): this handle holds the slices of ONE strip of element rows
@@ -561,31 +566,47 @@ static void compute_ranges(maf_handle* h) {
   if (!order.empty()) CU(cudaMemcpy(h->d_order, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
 }
 
-static void ensure_strips(maf_handle* h, int nstrips) {
-  if (!h->strips.empty()) return;
+// does the atomics path of this handle's range run in sub-strips? (large, row-aligned ranges)
+static bool wants_strips(const maf_handle* h) {
   const HostModel& M = h->M;
-  CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  int64_t min_elems = 32768;
+  if (const char* e = std::getenv("MAF_PIPELINE_MIN_ELEMS")) min_elems = std::atoll(e);
+  return h->e1 - h->e0 >= min_elems && h->e0 % M.num1el == 0 && h->e1 % M.num1el == 0 &&
+         (h->e1 - h->e0) / M.num1el >= 16;
+}
+
+static void ensure_strips(maf_handle* h, int nstrips) {
+  if (!h->strips.empty() && h->strips_e0 == h->e0 && h->strips_e1 == h->e1) return;
+  const HostModel& M = h->M;
+  for (auto& st : h->strips) cudaFree(st.d_order);
+  h->strips.clear();
+  h->strips_e0 = h->e0;
+  h->strips_e1 = h->e1;
+  if (!h->copy_stream) CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  const int64_t row0 = h->e0 / M.num1el, nrows = (h->e1 - h->e0) / M.num1el;
   for (int q = 0; q < nstrips; ++q) {
-    const int64_t r0 = ((int64_t)q * M.num2el) / nstrips, r1 = ((int64_t)(q + 1) * M.num2el) / nstrips;
+    const int64_t r0 = row0 + ((int64_t)q * nrows) / nstrips, r1 = row0 + ((int64_t)(q + 1) * nrows) / nstrips;
     if (r1 <= r0) continue;
     maf_handle::Strip st;
     st.e0 = r0 * M.num1el;
     st.e1 = r1 * M.num1el;
-    int64_t lo = M.numnp;
-    for (int64_t k = 9 * st.e0; k < 9 * st.e1; ++k) lo = std::min<int64_t>(lo, M.IX0[k]);
-    int64_t eq_lo = M.nmdf;
-    for (int64_t k = lo * M.ndf; k < M.numnp * M.ndf; ++k)
-      if (M.ID0[k] >= 0) { eq_lo = M.ID0[k]; break; }
-    st.eq_lo = eq_lo;
-    st.slot_lo = M.sym.colptr[eq_lo];
+    const TouchedRange R = touched_range(M, st.e0, st.e1);
+    st.eq_lo = R.eq_lo;
+    st.slot_lo = R.slot_lo;
+    st.eq_hi = R.eq_hi;
+    st.slot_hi = R.slot_hi;
     std::vector<int32_t> order;
     build_element_order(M.num1el, st.e0, st.e1, order);
     CU(cudaMalloc(&st.d_order, order.size() * sizeof(int32_t)));
     CU(cudaMemcpy(st.d_order, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     h->strips.push_back(st);
-    cudaEvent_t e;
-    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    h->strip_ev.push_back(e);
+    if (h->strip_ev.size() < h->strips.size()) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->strip_ev.push_back(e);
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->zero_ev.push_back(e);
+    }
   }
 }
 
@@ -683,30 +704,6 @@ static void ensure_stage(maf_handle* h) {
   }
 }
 
-// area + boundary kernels of the elements [e0, e1) on the atomics path (outputs must have been zeroed)
-static void launch_atomic_range(maf_handle* h, const double* d_xms, const double* d_cps, double time, double dt,
-                                double bend_tm, double* d_r, double* d_nz, cudaStream_t s, int64_t e0, int64_t e1,
-                                const int32_t* d_order) {
-  const HostModel& M = h->M;
-  area_fn kern = area_kernel_of(M.motion);
-  const int64_t ne = e1 - e0;
-  if (ne <= 0) return;
-  const int grid = (int)std::min<int64_t>(ne, (int64_t)h->grid);
-  StageSink st{nullptr, nullptr, 0, 0};
-  kern<<<grid, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, d_order, e0, e1);
-  CU(cudaGetLastError());
-  h->launches += 1;
-  for (int bc = 0; bc < M.n_neu; ++bc) {
-    const int n = M.b_offs[bc + 1] - M.b_offs[bc];
-    if (n == 0) continue;
-    const double fval = neumann_value(M.b_type[bc], M.b_val[bc], time, bend_tm);
-    const int gb = std::min((n + 3) / 4, h->sm_count * 8);
-    boundary_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, h->BT, bc, fval, dt, d_xms, d_r, d_nz, -1, 1, e0, e1);
-    CU(cudaGetLastError());
-    h->launches += 1;
-  }
-}
-
 // timing events: while a stream is being captured into a graph they are recorded as external event nodes, so that the
 // replayed graph keeps producing the per-phase device times
 static void rec(cudaEvent_t e, cudaStream_t s, bool capturing) {
@@ -725,6 +722,60 @@ static int enqueue_assembly(maf_handle* h, const double* d_xms, const double* d_
   const int grid = (int)std::min<int64_t>(std::max<int64_t>(ne, 1), (int64_t)h->grid);
   rec(h->ev[1], s, capturing);
   StageSink st{nullptr, nullptr, 0, 0};
+  const bool substrips = mode == MAF_SCATTER_ATOMIC && !capturing && h->side_stream && !h->strips.empty() &&
+                         h->strips_e0 == h->e0 && h->strips_e1 == h->e1;
+  if (substrips) {
+    // Large range: sub-strips of element rows, assembled one after the other. Only the first one waits for its
+    // zero-fill; the slots of the later ones (disjoint: everything above what the earlier strips touch) are zeroed on
+    // the second stream while the first strip is being assembled -- the 3 % of a step the zero-fill used to cost --
+    // followed there by the Neumann boundary kernels. Every strip records an event when its ranges are final
+    // (maf_assemble copies them to the host while the next strip runs).
+    const size_t ns = h->strips.size();
+    CU(cudaMemsetAsync(d_r + h->eq_lo, 0, sizeof(double) * (size_t)(h->eq_hi - h->eq_lo), s));
+    CU(cudaMemsetAsync(d_nz + h->slot_lo, 0, sizeof(double) * (size_t)(h->strips[0].slot_hi - h->slot_lo), s));
+    rec(h->ev[6], s, false);
+    CU(cudaEventRecord(h->ev_side[1], s));
+    CU(cudaStreamWaitEvent(h->side_stream, h->ev_side[1], 0));
+    for (size_t q = 1; q < ns; ++q) {
+      const int64_t lo = h->strips[q - 1].slot_hi, hi = h->strips[q].slot_hi;
+      if (hi > lo) CU(cudaMemsetAsync(d_nz + lo, 0, sizeof(double) * (size_t)(hi - lo), h->side_stream));
+      CU(cudaEventRecord(h->zero_ev[q], h->side_stream));
+    }
+    for (int bc = 0; bc < M.n_neu; ++bc) {
+      const int n = M.b_offs[bc + 1] - M.b_offs[bc];
+      if (n == 0) continue;
+      const double fval = neumann_value(M.b_type[bc], M.b_val[bc], time, bend_tm);
+      const int gb = std::min((n + 3) / 4, h->sm_count * 8);
+      boundary_kernel<<<gb, 128, 0, h->side_stream>>>(M.cfg, h->T, h->BT, bc, fval, dt, d_xms, d_r, d_nz, -1, 1, h->e0, h->e1);
+      CU(cudaGetLastError());
+      h->launches += 1;
+    }
+    CU(cudaEventRecord(h->ev_side[0], h->side_stream));
+    const int q0 = (int)(h->ring_n % MAF_RING);
+    rec(h->ring_a[q0], s, false);
+    for (size_t q = 0; q < ns; ++q) {
+      const maf_handle::Strip& sp = h->strips[q];
+      if (q > 0) CU(cudaStreamWaitEvent(s, h->zero_ev[q], 0));
+      const int gq = (int)std::min<int64_t>(sp.e1 - sp.e0, (int64_t)h->grid);
+      kern<<<gq, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, sp.d_order, sp.e0, sp.e1);
+      CU(cudaGetLastError());
+      h->launches += 1;
+      if (q == 0) CU(cudaStreamWaitEvent(s, h->ev_side[0], 0));   // (the boundary terms are long done by then)
+      CU(cudaEventRecord(h->strip_ev[q], s));
+    }
+    rec(h->ring_b[q0], s, false);
+    h->ring_n += 1;
+    rec(h->ev[2], s, false);
+    rec(h->ev[3], s, false);
+    rec(h->ev[4], s, false);
+    if (d_rn) {
+      rnorm2_partial<<<256, 256, 0, s>>>(d_r, M.nmdf, h->d_part);
+      rnorm2_final<<<1, 256, 0, s>>>(h->d_part, 256, d_rn);
+      CU(cudaGetLastError());
+      h->launches += 2;
+    }
+    return (int)(h->launches - launches0);
+  }
   if (mode == MAF_SCATTER_ATOMIC) {
     // only what this element range touches (contiguous, because unknowns are numbered node-major)
     if (d_r == h->d_r && d_nz == h->d_nz && !h->strip && h->eq_lo == 0 && h->eq_hi == M.nmdf && h->slot_lo == 0 &&
@@ -872,10 +923,19 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
   if (mode == MAF_SCATTER_DETERMINISTIC) {   // allocations and uploads: never inside a capture
     ensure_gather(h);
     ensure_stage(h);
+  } else if (h->host_copy_follows && wants_strips(h)) {
+    // (measured on the 1001 x 1001 workload, device part alone: 1 piece 39.60 ms, 4 strips 39.64, 8 strips 40.02,
+    // 16 strips 40.60 -- the hidden zero-fill is paid back in kernel tails; what pays is the copy-out of a
+    // finished strip running beside the next strips' kernels)
+    int ns = 8;
+    if (const char* e = std::getenv("MAF_SUBSTRIPS")) ns = std::max(1, std::atoi(e));
+    ensure_strips(h, ns);
+  } else if (!h->strips.empty()) {
+    h->strips_e0 = h->strips_e1 = -1;   // the range changed to one that is assembled in one piece
   }
   const bool graphable = h->use_graph && !h->strip && s == h->stream && d_r == h->d_r && d_nz == h->d_nz &&
                          d_xms == h->d_xms && d_cps == h->d_cps && (d_rn == nullptr || d_rn == h->d_rn) &&
-                         M.numel <= MAF_GRAPH_MAX_ELEMS;
+                         M.numel <= MAF_GRAPH_MAX_ELEMS && !(mode == MAF_SCATTER_ATOMIC && h->host_copy_follows && wants_strips(h));
   if (!graphable) {
     enqueue_assembly(h, d_xms, d_cps, time, dt, bend_tm, mode, d_r, d_nz, d_rn, s, false);
     h->timed_valid = true;
@@ -1166,6 +1226,7 @@ int maf_destroy(maf_handle* h) {
   if (h->d_order) cudaFree(h->d_order);
   for (auto& st : h->strips) cudaFree(st.d_order);
   for (auto& e : h->strip_ev) cudaEventDestroy(e);
+  for (auto& e : h->zero_ev) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->d_kel) cudaFree(h->d_kel);
   if (h->d_rel) cudaFree(h->d_rel);
@@ -1250,15 +1311,20 @@ static void assemble_to_host(maf_handle* h, double time, double dt, double bend_
   const HostModel& M = h->M;
   cudaStream_t s = h->stream;
   const size_t br = sizeof(double) * (size_t)M.nmdf, bk = sizeof(double) * (size_t)M.sym.nnz;
-  const bool full = h->e0 == 0 && h->e1 == M.numel;
-  // strips pay off once the device-to-host copy of nzval dominates; MAF_PIPELINE_MIN_ELEMS overrides the threshold
-  // (tests force the pipelined path on a small mesh with it)
-  int64_t min_elems = 32768;
-  if (const char* e = std::getenv("MAF_PIPELINE_MIN_ELEMS")) min_elems = std::atoll(e);
-  const bool pipelined = scatter_mode == MAF_SCATTER_ATOMIC && full && M.numel >= min_elems && M.num2el >= 16;
-  if (!pipelined) {
+  // Large ranges on the atomics path are assembled in sub-strips of element rows (enqueue_assembly): everything
+  // below the first slot a later strip touches is final once a strip is done, so its device-to-host copy (the
+  // dominant cost: nnz * 8 bytes over PCIe) overlaps the next strips.
+  const bool pipelined = scatter_mode == MAF_SCATTER_ATOMIC && h->e0 == 0 && h->e1 == M.numel && wants_strips(h);
+  h->host_copy_follows = pipelined;
+  try {
     do_assemble_device(h, h->d_xms, h->d_cps, time, dt, bend_tm, scatter_mode, h->d_r, h->d_nz,
                        rnorm2 ? h->d_rn : nullptr, s, true);
+  } catch (...) {
+    h->host_copy_follows = false;
+    throw;
+  }
+  h->host_copy_follows = false;
+  if (!pipelined) {
     // results straight into the caller's buffers (pageable destinations are staged by the driver)
     CU(cudaMemcpyAsync(r, h->d_r, br, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(nzval, h->d_nz, bk, cudaMemcpyDeviceToHost, s));
@@ -1266,25 +1332,7 @@ static void assemble_to_host(maf_handle* h, double time, double dt, double bend_
     CU(cudaEventRecord(h->ev[5], s));
     CU(cudaStreamSynchronize(s));
   } else {
-    // strips of element rows: everything below the first slot a later strip touches is final once a strip is
-    // done, so its device-to-host copy (the dominant cost: nnz * 8 bytes over PCIe) overlaps the next strips
-    ensure_strips(h, 8);
-    if (!(dt == dt) || !(time == time)) throw std::runtime_error("time / dt is NaN");
-    h->timed_valid = false;
-    CU(cudaEventRecord(h->ev[1], s));
-    CU(cudaMemsetAsync(h->d_r, 0, br, s));
-    CU(cudaMemsetAsync(h->d_nz, 0, bk, s));
-    CU(cudaEventRecord(h->ev[6], s));
     const size_t ns = h->strips.size();
-    for (size_t q = 0; q < ns; ++q) {
-      const maf_handle::Strip& st = h->strips[q];
-      launch_atomic_range(h, h->d_xms, h->d_cps, time, dt, bend_tm, h->d_r, h->d_nz, s, st.e0, st.e1, st.d_order);
-      CU(cudaEventRecord(h->strip_ev[q], s));
-    }
-    CU(cudaEventRecord(h->ev[2], s));
-    CU(cudaEventRecord(h->ev[3], s));
-    CU(cudaEventRecord(h->ev[4], s));
-    h->timed_valid = true;
     for (size_t q = 0; q < ns; ++q) {
       const int64_t s_lo = q == 0 ? 0 : h->strips[q].slot_lo, s_hi = q + 1 < ns ? h->strips[q + 1].slot_lo : M.sym.nnz;
       const int64_t r_lo = q == 0 ? 0 : h->strips[q].eq_lo, r_hi = q + 1 < ns ? h->strips[q + 1].eq_lo : M.nmdf;
@@ -1296,14 +1344,8 @@ static void assemble_to_host(maf_handle* h, double time, double dt, double bend_
         CU(cudaMemcpyAsync(r + r_lo, h->d_r + r_lo, sizeof(double) * (size_t)(r_hi - r_lo), cudaMemcpyDeviceToHost,
                            h->copy_stream));
     }
-    if (rnorm2) {
-      rnorm2_partial<<<256, 256, 0, s>>>(h->d_r, M.nmdf, h->d_part);
-      rnorm2_final<<<1, 256, 0, s>>>(h->d_part, 256, h->d_rn);
-      CU(cudaGetLastError());
-      h->launches += 2;
-      // (a copy into pageable host memory blocks the host until the stream drains: issue it last)
-      CU(cudaMemcpyAsync(rnorm2, h->d_rn, sizeof(double), cudaMemcpyDeviceToHost, s));
-    }
+    // (a copy into pageable host memory blocks the host until the stream drains: issue it last)
+    if (rnorm2) CU(cudaMemcpyAsync(rnorm2, h->d_rn, sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(h->copy_stream));
     CU(cudaEventRecord(h->ev[5], s));
     CU(cudaStreamSynchronize(s));
