@@ -380,6 +380,8 @@ def run(a, out_stream):
         d_r = torch.zeros(mesh.nmdf, dtype=torch.float64, device=dev)
         d_k = torch.zeros(asm.nnz, dtype=torch.float64, device=dev)
     d_n = torch.zeros(1, dtype=torch.float64, device=dev)
+    d_n2 = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(2)]
+    nstep, pending = [0], [None, None]
     torch.cuda.synchronize()
     mem_used = free0 - torch.cuda.mem_get_info(dev)[0]
     # everything (kernels, interface copies, NCCL ops, timing events) is ordered on the handle's own stream
@@ -393,9 +395,24 @@ def run(a, out_stream):
                                 d_nzval=d_k.data_ptr(), d_rnorm2=d_n.data_ptr(), stream=None)
         else:
             # kernels of the strip, interface sums pulled from the lower neighbour's memory over NVLink, partial |r|^2
+            # The one NCCL collective of a step, the residual norm, runs on NCCL's stream beside the next step's
+            # zero-fill and kernels (two norm buffers, used alternately); the last one is awaited inside the timed
+            # region (drain()).
+            slot = nstep[0] % 2
+            nstep[0] += 1
+            if pending[slot] is not None:
+                pending[slot].wait()
             asm.assemble_strip(d_x.data_ptr(), d_c.data_ptr(), dt, dt, scatter_mode=mode,
-                               d_rnorm2_partial=d_n.data_ptr())
-            dist.all_reduce(d_n)          # the one NCCL collective of a step: the residual norm
+                               d_rnorm2_partial=d_n2[slot].data_ptr())
+            pending[slot] = dist.all_reduce(d_n2[slot], async_op=True)
+
+    def drain():
+        for k in range(2):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
+        if world > 1 and nstep[0] > 0:
+            d_n.copy_(d_n2[(nstep[0] - 1) % 2])
 
     def barrier():
         torch.cuda.synchronize()
@@ -410,6 +427,7 @@ def run(a, out_stream):
         sampler.start()
     for _ in range(a.warmup):
         step()
+    drain()
     barrier()
     s_first = sampler.mark()
     l0 = asm.launch_count()
@@ -417,6 +435,7 @@ def run(a, out_stream):
     ev0.record()
     for _ in range(a.steps):          # no host synchronisation inside the timed region
         step()
+    drain()
     ev1.record()
     barrier()
     # device time of the dominant kernel in every launch of the timed region (event ring inside the library), and the
@@ -448,6 +467,7 @@ def run(a, out_stream):
         for _ in range(int(max(1.0, 400.0 / max(ms / a.steps, 1e-3)))):   # ~0.4 s of the same steps
             step()
             extra += 1
+        drain()
         barrier()
     clocks = sampler.stop(s_first) if rank == 0 else None
     if clocks is not None and extra:
@@ -597,8 +617,11 @@ def run(a, out_stream):
                 "fp64": {"achieved_tflops": ach_tf, "peak_tflops": fp64_peak, "frac": ach_tf / fp64_peak,
                          "algorithmic_flop_per_element": F_EL[a.motion],
                          "peak_source": "maf_fp64_peak DFMA microbenchmark, this run",
-                         "note": "the kernel is FP64 CUDA-core bound (arithmetic intensity ~32 FLOP/B vs machine "
-                                 "balance ~5); the HBM fraction above is the schema's headline, this is the binding one"},
+                         "note": "the kernel runs on the FP64 CUDA cores and is on the compute side of the roofline "
+                                 "(arithmetic intensity ~32 FLOP/B vs machine balance ~5): the HBM fraction above is "
+                                 "the schema's headline, this one is the relevant ceiling. What limits it below the "
+                                 "DFMA peak (ncu, DESIGN.md section 4): the shared-memory data pipe (69 %) and the "
+                                 "latency chain of the Gauss-point items at 3 resident CTAs per SM"},
                 "other_kernels_ms": other}
 
     # ---- everything that needs the oracle runs in child processes (this process maps libmembrane_b200.so only) ---

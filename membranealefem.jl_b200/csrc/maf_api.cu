@@ -480,6 +480,8 @@ struct maf_handle {
   // small meshes: the launch sequence of an assembly, captured once per key and replayed (do_assemble_device)
   struct Band { int64_t e0, e1; int32_t* d_order; };   // deterministic path: bands of element rows (ensure_stage)
   std::vector<Band> bands;
+  std::vector<cudaEvent_t> band_staged, band_gathered;   // one pair per band (ordering only, no timing)
+  cudaStream_t gather_stream = nullptr;                  // high priority: a band's gather runs beside the next band
   int64_t band_rows = 0, band_e0 = -1, band_e1 = -1;
   struct Graph { std::vector<double> key; cudaGraphExec_t exec = nullptr; int launches = 0; };
   std::vector<Graph> graphs;
@@ -631,12 +633,15 @@ static void ensure_gather(maf_handle* h) {
 }
 
 // Staging of the deterministic path. A staged element takes (81 nij + 72) doubles, 3.4 times its share of nzval, so
-// large ranges are staged in BANDS of element rows: a band is assembled into a ring that holds two bands, then every
-// node row whose contributing element rows (n - 2 .. n) are all staged is gathered, in ascending order. The ring is
-// sized to ~6 % of the range's nzval; small ranges keep one block per element (a single band).
+// large ranges are staged in BANDS of element rows: a band is assembled into a ring that holds three bands, then every
+// node row whose contributing element rows (n - 2 .. n) are all staged is gathered, in ascending order -- on a second,
+// high-priority stream, while the next band is being assembled into the third ring slot (the gather of band b reads
+// the slots of b - 1 and b; band b + 2 reuses the slot of b - 1 and waits for that gather). The ring is sized to ~8 %
+// of the range's nzval; small ranges keep one block per element (a single band).
 #ifndef MAF_BAND_MIN_ELEMS
 #define MAF_BAND_MIN_ELEMS 65536
 #endif
+#define MAF_RING_BANDS 3
 static void ensure_stage(maf_handle* h) {
   const HostModel& M = h->M;
   const size_t ne = (size_t)(h->e1 - h->e0);
@@ -646,8 +651,8 @@ static void ensure_stage(maf_handle* h) {
     const int64_t nrows = (int64_t)ne / M.num1el;
     const double per_el = ((double)81 * h->nij + 72) * sizeof(double);
     const double nz_bytes = (double)(h->slot_hi - h->slot_lo) * sizeof(double);
-    band_rows = std::max<int64_t>(4, (int64_t)(0.06 * nz_bytes / (2.0 * per_el * M.num1el)));
-    if (band_rows * 2 >= nrows) band_rows = 0;
+    band_rows = std::max<int64_t>(4, (int64_t)(0.08 * nz_bytes / (MAF_RING_BANDS * per_el * M.num1el)));
+    if (band_rows * MAF_RING_BANDS >= nrows) band_rows = 0;
   }
   if (band_rows) {   // the band arithmetic relies on the structured node numbering of the reference's patches
     const int64_t num1np = M.num1el + 2;
@@ -667,7 +672,7 @@ static void ensure_stage(maf_handle* h) {
         if (M.IX0[9 * el + a] != (el % M.num1el + a % 3) + num1np * (el / M.num1el + a / 3)) { ok = false; break; }
     if (!ok) band_rows = 0;
   }
-  const size_t need_elems = band_rows ? (size_t)(2 * band_rows * M.num1el) : ne;
+  const size_t need_elems = band_rows ? (size_t)(MAF_RING_BANDS * band_rows * M.num1el) : ne;
   if (h->d_kel && h->kel_elems >= need_elems && h->band_rows == band_rows && h->band_e0 == h->e0 && h->band_e1 == h->e1)
     return;
   if (h->d_kel) {
@@ -700,6 +705,18 @@ static void ensure_stage(maf_handle* h) {
       CU(cudaMalloc(&b.d_order, order.size() * sizeof(int32_t)));
       CU(cudaMemcpy(b.d_order, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
       h->bands.push_back(b);
+    }
+    if (!h->gather_stream) {
+      int least = 0, greatest = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      CU(cudaStreamCreateWithPriority(&h->gather_stream, cudaStreamNonBlocking, greatest));
+    }
+    while (h->band_staged.size() < h->bands.size()) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->band_staged.push_back(e);
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->band_gathered.push_back(e);
     }
   }
 }
@@ -841,33 +858,40 @@ static int enqueue_assembly(maf_handle* h, const double* d_xms, const double* d_
     h->launches += 2;
   }
   if (banded) {
-    // band after band: stage the band's elements (ring of two bands), then gather the node rows that are complete.
+    // band after band: stage the band's elements (ring of three bands), then gather the node rows that are complete
     // Node row n of the patch takes contributions from the element rows n - 2 .. n only (quadratic splines).
     GatherTables G = h->G;
     G.ring = (int64_t)h->kel_elems;
     const int64_t num1np = M.num1el + 2;          // node rows are num1el + 2 nodes long (IX of Mesh.jl:574-593)
     int64_t node_done = h->node_lo;               // first node not gathered yet
     const int gb = h->sm_count * 16;
+    cudaStream_t gs = h->gather_stream;
     for (size_t b = 0; b < h->bands.size(); ++b) {
       const maf_handle::Band& B = h->bands[b];
       const int gridb = (int)std::min<int64_t>(B.e1 - B.e0, (int64_t)h->grid);
+      // the ring slot of this band was last read by the gather of band b - 2
+      if (b >= MAF_RING_BANDS - 1) CU(cudaStreamWaitEvent(s, h->band_gathered[b - (MAF_RING_BANDS - 1)], 0));
       // (the area kernel indexes the staging ring by el - e0 of the RANGE: pass the range start with the band's order)
       kern<<<gridb, MAF_NT, h->smem_bytes, s>>>(M.cfg, h->T, d_xms, d_cps, dt, d_r, d_nz, st, B.d_order, h->e0,
                                               h->e0 + (B.e1 - B.e0));
       CU(cudaGetLastError());
+      h->launches += 1;
+      CU(cudaEventRecord(h->band_staged[b], s));
+      CU(cudaStreamWaitEvent(gs, h->band_staged[b], 0));
       const bool last = b + 1 == h->bands.size();
       // complete node rows: up to (first element row of the next band) - 1, i.e. all nodes below that row's first node
       const int64_t node_hi = last ? h->node_hi : std::min<int64_t>(h->node_hi, (B.e1 / M.num1el) * num1np);
       if (node_hi > node_done) {
-        gather_K_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, G, h->d_kel, h->nij, h->e0, h->e1, M.sym.nbr_ptr[node_done],
-                                          M.sym.nbr_ptr[node_hi], d_nz);
-        gather_r_kernel<<<gb, 128, 0, s>>>(M.cfg, h->T, G, h->d_rel, h->e0, h->e1, node_done * M.ndf, node_hi * M.ndf, d_r);
+        gather_K_kernel<<<gb, 128, 0, gs>>>(M.cfg, h->T, G, h->d_kel, h->nij, h->e0, h->e1, M.sym.nbr_ptr[node_done],
+                                           M.sym.nbr_ptr[node_hi], d_nz);
+        gather_r_kernel<<<gb, 128, 0, gs>>>(M.cfg, h->T, G, h->d_rel, h->e0, h->e1, node_done * M.ndf, node_hi * M.ndf, d_r);
         CU(cudaGetLastError());
         node_done = node_hi;
         h->launches += 2;
       }
-      h->launches += 1;
+      CU(cudaEventRecord(h->band_gathered[b], gs));
     }
+    if (!h->bands.empty()) CU(cudaStreamWaitEvent(s, h->band_gathered[h->bands.size() - 1], 0));
   }
   rec(h->ev[3], s, capturing);
   if (side) CU(cudaStreamWaitEvent(s, h->ev_side[0], 0));
@@ -1227,6 +1251,9 @@ int maf_destroy(maf_handle* h) {
   for (auto& st : h->strips) cudaFree(st.d_order);
   for (auto& e : h->strip_ev) cudaEventDestroy(e);
   for (auto& e : h->zero_ev) cudaEventDestroy(e);
+  for (auto& e : h->band_staged) cudaEventDestroy(e);
+  for (auto& e : h->band_gathered) cudaEventDestroy(e);
+  if (h->gather_stream) { cudaStreamSynchronize(h->gather_stream); cudaStreamDestroy(h->gather_stream); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->d_kel) cudaFree(h->d_kel);
   if (h->d_rel) cudaFree(h->d_rel);

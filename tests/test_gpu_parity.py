@@ -386,7 +386,7 @@ def test_graph_replay_equals_plain_launches(monkeypatch):
 @pytest.mark.parametrize("name,rows", [("alevb_pull_17x17", 2), ("alevb_pull_17x17", 5), ("lag_pull_17x17", 3),
                                        ("alevb_pull_fine_19x18", 4)])
 def test_banded_deterministic_staging(monkeypatch, name, rows):
-    """Large ranges stage the deterministic path band by band of element rows (ring of two bands, ~6 % of nzval
+    """Large ranges stage the deterministic path band by band of element rows (ring of three bands, ~8 % of nzval
     instead of 3.4 x nzval): forced on small meshes with MAF_BAND_ROWS, bitwise equal to the unbanded path (same
     ascending-element-id sums), also on a strip of a 2-strip partition."""
     p, hm, om, xms, cps, time, dt, args = make_case(name)
