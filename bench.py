@@ -559,15 +559,17 @@ def run(a, out_stream):
         dist.all_reduce(nb)
         # host-link roofline of this box for this traffic: every rank copies its owned nzval slice to pinned host
         # memory at the same time, nothing else running (what the e2e step cannot beat)
-        barrier()
-        reps = 3
-        t0 = time.perf_counter()
-        for _ in range(reps):
+        # (one untimed repetition first; then the best of three, each the max over ranks of a copy started together)
+        link_s = float("inf")
+        for rep in range(4):
+            barrier()
+            t0 = time.perf_counter()
             asm.download(1, 0, sinfo["own_slots"][0], own_k, nz_out=hk.numpy())
-        torch.cuda.synchronize()
-        tl = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
-        link_s = float(tl.item()) / reps
+            torch.cuda.synchronize()
+            tl = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+            if rep > 0:
+                link_s = min(link_s, float(tl.item()))
         kb = torch.tensor([own_k * 8], dtype=torch.int64, device=dev)
         dist.all_reduce(kb)
         link_gbs = float(kb.item()) / link_s / 1e9
@@ -583,7 +585,9 @@ def run(a, out_stream):
                "host_link_roofline": {"aggregate_d2h_gbs": link_gbs, "ms_for_nzval": link_s * 1e3,
                                       "e2e_fraction_of_link_roofline": link_s / e2e_s,
                                       "how": f"{world} ranks copy their owned nzval slices to pinned host memory "
-                                             "concurrently, nothing else running; max over ranks"}}
+                                             "concurrently, nothing else running; max over ranks, best of 3 "
+                                             "(a reference point measured with one plain copy per rank: the strip "
+                                             "pipeline of the e2e call can come out slightly ahead of it)"}}
 
     if rank != 0:
         if world > 1:
