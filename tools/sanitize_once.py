@@ -46,5 +46,21 @@ for motion, n in ((maf.ALEVB, 19), (maf.LAG, 9), (maf.EUL, 7), (maf.ALEV, 7), (m
         rb, nzb, _ = band.assemble(xms, cps, 0.5, 0.5, scatter_mode=maf.SCATTER_DETERMINISTIC)
         assert np.array_equal(nzb, nz)
         band.close()
-        del os.environ["MAF_BAND_ROWS"], os.environ["MAF_NO_GRAPH"]
+        del os.environ["MAF_BAND_ROWS"]
+        # banded staging inside a captured graph (gathers on the second stream), sub-strips with the pipelined copy-out
+        del os.environ["MAF_NO_GRAPH"]
+        os.environ["MAF_BAND_ROWS"] = "2"
+        band = maf.Assembler(mesh, p)
+        for _ in range(2):
+            rb, nzb, _ = band.assemble(xms, cps, 0.5, 0.5, scatter_mode=maf.SCATTER_DETERMINISTIC)
+        assert np.array_equal(nzb, nz)
+        band.close()
+        del os.environ["MAF_BAND_ROWS"]
+        if n >= 17:
+            os.environ["MAF_PIPELINE_MIN_ELEMS"] = "1"
+            pipe = maf.Assembler(mesh, p)
+            rp, nzp, _ = pipe.assemble(xms, cps, 0.5, 0.5)
+            assert np.abs(nzp - nz).max() <= 1e-12 * np.abs(nz).max()
+            pipe.close()
+            del os.environ["MAF_PIPELINE_MIN_ELEMS"]
     print("ok", int(motion), n, float(rn))
