@@ -115,7 +115,10 @@ int maf_pattern_columns(maf_handle* h, int64_t col_first, int64_t col_last, int6
  *   r    nmdf            out: r_gl
  *   nzval nnz            out: K_gl.nzval in the order of maf_pattern
  *   rnorm2 (optional)    out: sum(r.^2)
- * bend_tm is args[:bend_tm] (only read for MOMENT conditions, FiniteElement.jl:379). */
+ * bend_tm is args[:bend_tm] (only read for MOMENT conditions, FiniteElement.jl:379).
+ * From 32768 elements on (MAF_PIPELINE_MIN_ELEMS) the atomics path assembles the mesh in sub-strips of element rows
+ * (8; MAF_SUBSTRIPS) and copies the finished ranges of r / nzval to the host while the next strips are being
+ * assembled; page-locked destinations (maf_host_register) make those copies asynchronous. */
 int maf_assemble(maf_handle* h, const double* xms, const double* cps, double time, double dt, double bend_tm,
                  int scatter_mode, double* r, double* nzval, double* rnorm2);
 
@@ -154,7 +157,8 @@ int maf_area_kernel_times(maf_handle* h, double* out_ms, int64_t n);
  * out[6] assemblies replayed from a captured CUDA graph so far (meshes of <= 16384 elements assembling into the
  * handle's own buffers: their ~10 launches are bound by the host's launch rate; MAF_NO_GRAPH=1 disables it),
  * out[7] bytes of staging memory the deterministic path holds (0 until it ran), out[8] its band height in element
- * rows (0 = the whole range staged at once; large ranges are staged in bands, ~6 % of nzval). */
+ * rows (0 = the whole range staged at once; large ranges are staged in a ring of three bands, ~8 % of nzval;
+ * MAF_BAND_ROWS overrides the height). */
 int maf_kernel_info(maf_handle* h, int64_t* out9);
 
 /* The static plan of the area kernel's contraction phase as text: "c,c,c/c,c/..." = the chunk ids (<= 32 tangent
