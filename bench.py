@@ -527,6 +527,19 @@ def run(a, out_stream):
                        "the host solver needs) inside the timed region (CUDA events on the handle's stream)"}
         err = float(np.abs(hr.numpy() - d_r.cpu().numpy()).max())
         e2e["max_abs_diff_r_vs_device_path"] = err
+        # host-link roofline of this box for this traffic: one plain pinned device-to-host copy of nzval, nothing else
+        # running (what the e2e call cannot beat: its copies hide the kernels, not the other way round)
+        link_s = float("inf")
+        for rep in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            asm.download(1, 0, 1, asm.nnz, nz_out=hk.numpy())
+            torch.cuda.synchronize()
+            if rep > 0:
+                link_s = min(link_s, time.perf_counter() - t0)
+        e2e["host_link_roofline"] = {"d2h_gbs": asm.nnz * 8 / link_s / 1e9, "ms_for_nzval": link_s * 1e3,
+                                     "e2e_fraction_of_link_roofline": link_s / (tot / a.steps * 1e-3),
+                                     "how": "one pinned device-to-host copy of nzval, best of 2 after a warm-up"}
     elif not a.no_e2e:
         # N > 1, through the strip handle's host-buffer entry point (maf_assemble_strip_host): every rank uploads the
         # node rows its strip reads from pinned host memory, assembles, takes part in the interface exchange and copies
