@@ -197,6 +197,10 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
       for (int k = 0; k < 3; ++k) items.push_back(Item{IT_GEO_B, (uint8_t)gp, (uint8_t)k, 0});
   }
   for (int gp = 0; gp < 9; ++gp) items.push_back(Item{IT_LIN, (uint8_t)gp, 0, 0});
+  // closed-form columns of the components of v / vm as their own items (maf_element.cuh::lin_split)
+  if (lin_split(motion))
+    for (int gp = 0; gp < 9; ++gp)
+      for (int j = 0; j < 3; ++j) items.push_back(Item{IT_LIN_C, (uint8_t)gp, 0, (uint8_t)j});
   if ((int)items.size() > MAF_MAX_ITEMS) throw std::runtime_error("item table overflow");
   cfg.nitems = (int)items.size();
   for (int k = 0; k < cfg.nitems; ++k) cfg.items[k] = items[k];
@@ -250,7 +254,9 @@ inline void build_config(Config& cfg, int motion, int ndf, const int32_t dofs8[8
     std::vector<int> cls(cfg.nitems), cost(cfg.nitems);
     for (int k = 0; k < cfg.nitems; ++k) {
       cls[k] = cfg.items[k].type;
-      cost[k] = cfg.items[k].type == IT_LIN ? 6 : 10;
+      const int ty = cfg.items[k].type;
+      if (lin_split(motion)) cost[k] = ty == IT_GEO_A ? 10 : (ty == IT_GEO_B ? 5 : (ty == IT_LIN ? 4 : 2));
+      else cost[k] = ty == IT_LIN ? 6 : 10;
     }
     schedule(cls, cost, {}, -1, cfg.item_slot, cfg.item_rounds);
   }

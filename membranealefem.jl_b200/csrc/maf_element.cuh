@@ -36,7 +36,29 @@ constexpr int kFusedUnroll = MAF_FUSED_UNROLL;
 namespace maf {
 
 enum { F_V = 0, F_M = 1, F_L = 2, F_P = 3, NFIELD = 4 };
-enum { IT_GEO_A = 0, IT_GEO_B = 1, IT_LIN = 2 };
+enum { IT_GEO_A = 0, IT_GEO_B = 1, IT_LIN = 2, IT_LIN_C = 3 };
+// Per motion, measured on the 1001 x 1001 patch (profiles/r2_variants.md): the ALE motions run the closed-form columns
+// of v / vm as their own items (IT_LIN_C) and take the metric tangent of the GEO_A items in closed form; EUL and LAG
+// are faster without either (both can be forced for all motions with -DMAF_LIN_SPLIT_ALL / -DMAF_CLOSED_GEOM_ALL,
+// or off with -DMAF_NO_LIN_SPLIT / -DMAF_NO_CLOSED_GEOM).
+MAF_HD constexpr bool lin_split(int motion) {
+#if defined(MAF_NO_LIN_SPLIT)
+  return false;
+#elif defined(MAF_LIN_SPLIT_ALL)
+  return motion != M_LAG && motion != M_STATIC;
+#else
+  return motion == M_ALEV || motion == M_ALEVB;
+#endif
+}
+MAF_HD constexpr bool closed_geom(int motion) {
+#if defined(MAF_NO_CLOSED_GEOM)
+  return false;
+#elif defined(MAF_CLOSED_GEOM_ALL)
+  return true;
+#else
+  return motion == M_ALEV || motion == M_ALEVB;
+#endif
+}
 
 struct Block {      // one (row field, col field) tangent block type
   int8_t f, g;      // row / col field
@@ -78,7 +100,7 @@ struct Item {       // phase-G work item of one Gauss point
 #define MAF_MAX_BLOCKS 14
 #define MAF_MAX_CHUNKS 48
 #define MAF_MAX_ROUNDS 16
-#define MAF_MAX_ITEMS 96
+#define MAF_MAX_ITEMS 128
 #define MAF_MAX_SLOTS 256
 
 struct Config {
@@ -517,6 +539,9 @@ MAF_HD void load_E(const double* E, double a[2][3], double c[3][3], double dv[2]
 //                       forward-mode b-directions + the closed-form Gamma term (-Q_k a^mu_j on the N_mu rows)
 //  IT_LIN             : primal S (residual), and the closed-form columns of the dofs that do not move the mesh
 //                       (the residual is affine in cps at fixed x)
+//  IT_LIN_C (j)       : the closed-form columns of component j of v / vm, split off the LIN item: with one lane per
+//                       Gauss point doing all of it the LIN warp was as long a chain as the GEO_A warps (removing
+//                       either alone from a timing build saves 4-6 % of the kernel, both 20 %)
 // ---------------------------------------------------------------------------------------------------------
 template <int MOTION>
 MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const double* fr, double* sm) {
@@ -537,33 +562,34 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const 
 #pragma unroll
       for (int i = 0; i < 3; ++i) ad[al][i] = Dual(a[al][i], (al == it.gamma && i == it.j) ? dt : 0.0);
     GpStress<Dual> S;
-#ifdef MAF_GEO_A_CLOSED_GEOM   // variant: metric tangent in closed form instead of dual numbers through gp_geom --
-                               // 48 FP64 instructions fewer per item, same results, measured 2 % (LAG 4 %) SLOWER
-                               // (profiles/r2_variants.md); kept for the record, off by default
-    GpGeom<double> g0;
-    gp_geom(a, g0);
-    GpGeom<Dual> gd;
-    gp_geom_tangent(g0, it.gamma, it.j, dt, gd);
-    if (MOTION == M_LAG) {  // mesh velocity = v
-      Dual dvd[2][3];
+    if (closed_geom(MOTION)) {
+      // metric tangent in closed form instead of dual numbers through gp_geom: 48 FP64 instructions fewer per item and
+      // no dual division / square root, same results. It pays only where the GEO_A warps are the one critical chain
+      // of the phase (ALE motions once the LIN item is split): ALEVB -1.7 %, ALEV -2.2 %, LAG / EUL +1-2 %
+      GpGeom<double> g0;
+      gp_geom(a, g0);
+      GpGeom<Dual> gd;
+      gp_geom_tangent(g0, it.gamma, it.j, dt, gd);
+      if (MOTION == M_LAG) {  // mesh velocity = v
+        Dual dvd[2][3];
 #pragma unroll
-      for (int al = 0; al < 2; ++al)
+        for (int al = 0; al < 2; ++al)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) dvd[al][i] = Dual(dv[al][i], (al == it.gamma && i == it.j) ? 1.0 : 0.0);
-      Dual vd[3] = {Dual(v[0]), Dual(v[1]), Dual(v[2])};
-      gp_eval_geom<MOTION, Dual, double, Dual, double, double>(gd, ad, c, dvd, vd, dm, vm, lam, pm, cfg.mat, S);
-    } else {               // mesh velocity = vm
-      Dual dmd[2][3];
+          for (int i = 0; i < 3; ++i) dvd[al][i] = Dual(dv[al][i], (al == it.gamma && i == it.j) ? 1.0 : 0.0);
+        Dual vd[3] = {Dual(v[0]), Dual(v[1]), Dual(v[2])};
+        gp_eval_geom<MOTION, Dual, double, Dual, double, double>(gd, ad, c, dvd, vd, dm, vm, lam, pm, cfg.mat, S);
+      } else {               // mesh velocity = vm
+        Dual dmd[2][3];
 #pragma unroll
-      for (int al = 0; al < 2; ++al)
+        for (int al = 0; al < 2; ++al)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) dmd[al][i] = Dual(dm[al][i], (al == it.gamma && i == it.j) ? 1.0 : 0.0);
-      Dual vmd[3] = {Dual(vm[0]), Dual(vm[1]), Dual(vm[2])};
-      gp_eval_geom<MOTION, Dual, double, double, Dual, double>(gd, ad, c, dv, v, dmd, vmd, lam, pm, cfg.mat, S);
+          for (int i = 0; i < 3; ++i) dmd[al][i] = Dual(dm[al][i], (al == it.gamma && i == it.j) ? 1.0 : 0.0);
+        Dual vmd[3] = {Dual(vm[0]), Dual(vm[1]), Dual(vm[2])};
+        gp_eval_geom<MOTION, Dual, double, double, Dual, double>(gd, ad, c, dv, v, dmd, vmd, lam, pm, cfg.mat, S);
+      }
+      store_column(cfg, Agp, w, S, mf, it.j, CH_N1 + it.gamma);
+      return;
     }
-    store_column(cfg, Agp, w, S, mf, it.j, CH_N1 + it.gamma);
-    return;
-#endif
     if (MOTION == M_LAG) {  // mesh velocity = v
       Dual dvd[2][3];
 #pragma unroll
@@ -588,6 +614,48 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const 
 
   GpGeom<double> g;
   gp_geom(a, g);
+  if (lin_split(MOTION) && it.type == IT_LIN_C) {
+    // (j is a per-lane run-time value: selected with conditionals, never by indexing -- an array indexed at run time
+    // would be placed in local memory)
+    const int j = it.j;
+    const double wJ = w * g.J, zv = cfg.mat.zv, am = cfg.mat.am;
+    const double Aup[2][2] = {{g.A11, g.A12}, {g.A12, g.A22}};
+    const double upj[2] = {j == 0 ? g.up[0][0] : (j == 1 ? g.up[0][1] : g.up[0][2]),
+                           j == 0 ? g.up[1][0] : (j == 1 ? g.up[1][1] : g.up[1][2])};
+    const double a0j = j == 0 ? a[0][0] : (j == 1 ? a[0][1] : a[0][2]);
+    const double a1j = j == 0 ? a[1][0] : (j == 1 ? a[1][1] : a[1][2]);
+    const double nj = j == 0 ? g.n[0] : (j == 1 ? g.n[1] : g.n[2]);
+    if (mf != F_V) {
+      // (v, j, N_mu): d pi^{ab}/d v_{,mu}_j = zv (a^a_j a^{mu b} + a^b_j a^{mu a})   =>
+      //   d Sv[N_al][i] = J zv (a^al_j a^mu_i + a^{mu al} (delta_ij - n_i n_j)),   d Sl = J a^mu_j
+#pragma unroll
+      for (int mu = 0; mu < 2; ++mu) {
+        const int d = CH_N1 + mu;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          // tangential projector delta_ij - n_i n_j, formed as a^mu_i a_mu_j: no cancellation of two O(1) terms, and
+          // exactly zero where the reference's complex step gives an exact zero (flat patch, i = j = z)
+          const double Pij = g.up[0][i] * a0j + g.up[1][i] * a1j;
+#pragma unroll
+          for (int al = 0; al < 2; ++al)
+            put(cfg, Agp, F_V, i, CH_N1 + al, F_V, j, d, wJ * zv * (upj[al] * g.up[mu][i] + Aup[mu][al] * Pij));
+        }
+        if (has_col(cfg, F_L, F_V, d)) Agp[a_index(cfg, F_L, 0, CH_N, F_V, j, d)] = wJ * upj[mu];
+      }
+      if (MOTION == M_EUL || ALE) {  // (v, j, N): EUL d Sm[N][i] = -am J n_i n_j ; ALE d Sp = +J n_j
+        if (MOTION == M_EUL) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) put(cfg, Agp, F_M, i, CH_N, F_V, j, CH_N, -wJ * am * g.n[i] * nj);
+        }
+        if (ALE && has_col(cfg, F_P, F_V, CH_N)) Agp[a_index(cfg, F_P, 0, CH_N, F_V, j, CH_N)] = wJ * nj;
+      }
+    }
+    if (MOTION == M_EUL || ALE) {    // (vm, j, N): EUL d Sm[N][i] = am J delta_ij ; ALE d Sp = -J n_j
+      if (MOTION == M_EUL) put(cfg, Agp, F_M, j, CH_N, F_M, j, CH_N, wJ * am);
+      if (ALE && has_col(cfg, F_P, F_M, CH_N)) Agp[a_index(cfg, F_P, 0, CH_N, F_M, j, CH_N)] = -wJ * nj;
+    }
+    return;
+  }
   double b[3], Gam[3][2];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -635,6 +703,9 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const 
   }
 #endif
 
+#if defined(MAF_STUB_LIN)   // timing-only build
+  return;
+#endif
   // ---- IT_LIN: primal stresses -> S[gp] ----
   GpStress<double> S;
   gp_core<MOTION>(g, a, b, Gam, dv, v, dm, vm, lam, pm, cfg.mat, S);
@@ -648,6 +719,7 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const 
   // ---- closed-form columns (all factors below are metric quantities of this Gauss point) ----
   const double wJ = w * g.J, zv = cfg.mat.zv, am = cfg.mat.am, kdb = cfg.mat.kdb;
   const double Aup[2][2] = {{g.A11, g.A12}, {g.A12, g.A22}};
+  if (!lin_split(MOTION)) {   // the columns of the three components on the LIN lane itself
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     if (mf != F_V) {
@@ -679,6 +751,7 @@ MAF_HD void phase_gauss_item(const Config& cfg, const Item it, double dt, const 
       if (MOTION == M_EUL) put(cfg, Agp, F_M, j, CH_N, F_M, j, CH_N, wJ * am);
       if (ALE && has_col(cfg, F_P, F_M, CH_N)) Agp[a_index(cfg, F_P, 0, CH_N, F_M, j, CH_N)] = -wJ * g.n[j];
     }
+  }
   }
   {  // (lambda, N): d Sv[N_al][i] = J a^al_i ; d Sl = -adb/zv
 #pragma unroll
@@ -1016,6 +1089,15 @@ MAF_HD void scatter_row(const Config& cfg, const double* fr, const KSink& sink, 
     for (int b = 0; b < 9; ++b) dst[(size_t)b * sink.nij] = acc[b];
     return;
   }
+#if defined(MAF_STUB_SCATTER)   // timing-only build: no slot look-up, no reductions (the sums keep the tasks alive)
+  {
+    double ssum = 0.0;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) ssum += acc[b];
+    if (ssum == 1.2345e-300) sink.nzval[0] = ssum;
+    return;
+  }
+#endif
   // atomics path: K_gl[LM[i], LM[j]] += K_el[i, j] for active rows and columns (FiniteElement.jl:129-136)
   const int32_t* si = reinterpret_cast<const int32_t*>(fr + cfg.o_int);
   const unsigned m = (unsigned)si[I_MASK + a];
@@ -1043,6 +1125,15 @@ MAF_HD void scatter_col(const Config& cfg, const double* fr, const KSink& sink, 
     for (int a = 0; a < 9; ++a) dst[(size_t)(9 * a) * sink.nij] = acc[a];
     return;
   }
+#if defined(MAF_STUB_SCATTER)
+  {
+    double ssum = 0.0;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) ssum += acc[a];
+    if (ssum == 1.2345e-300) sink.nzval[0] = ssum;
+    return;
+  }
+#endif
   const int32_t* sl = reinterpret_cast<const int32_t*>(fr + cfg.o_slot) + 81 * b + J;
   if (sl[0] < 0) return;   // columns exist only for active dofs (FiniteElement.jl:111)
   const int32_t* si = reinterpret_cast<const int32_t*>(fr + cfg.o_int);
