@@ -425,7 +425,11 @@ MAF_HD void phase_interp(int tid, int nt, const Config& cfg, const double* fr, d
   {
     dbl2* Az = reinterpret_cast<dbl2*>(sm + cfg.o_A);
     const dbl2 z = {0.0, 0.0};
+#ifndef MAF_STUB_AZERO   // (timing-only build without the zero-fill)
     for (int k = tid; k < 9 * cfg.asize / 2; k += nt) Az[k] = z;
+#else
+    if (tid == 0) Az[0] = z;
+#endif
     if (tid == 0) *reinterpret_cast<int*>(sm + cfg.o_ctr) = 0;   // chunk queue of the tangent phase
   }
   // One thread per (field q, Gauss row g2), sum-factorised over the tensor-product basis (gp = g1 + 3 g2,
