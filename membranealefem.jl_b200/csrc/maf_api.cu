@@ -739,8 +739,8 @@ static int enqueue_assembly(maf_handle* h, const double* d_xms, const double* d_
   const int grid = (int)std::min<int64_t>(std::max<int64_t>(ne, 1), (int64_t)h->grid);
   rec(h->ev[1], s, capturing);
   StageSink st{nullptr, nullptr, 0, 0};
-  const bool substrips = mode == MAF_SCATTER_ATOMIC && !capturing && h->side_stream && !h->strips.empty() &&
-                         h->strips_e0 == h->e0 && h->strips_e1 == h->e1;
+  const bool substrips = mode == MAF_SCATTER_ATOMIC && !capturing && h->host_copy_follows && h->side_stream &&
+                         !h->strips.empty() && h->strips_e0 == h->e0 && h->strips_e1 == h->e1;
   if (substrips) {
     // Large range: sub-strips of element rows, assembled one after the other. Only the first one waits for its
     // zero-fill; the slots of the later ones (disjoint: everything above what the earlier strips touch) are zeroed on
@@ -953,9 +953,7 @@ static void do_assemble_device(maf_handle* h, const double* d_xms, const double*
     // finished strip running beside the next strips' kernels)
     int ns = 8;
     if (const char* e = std::getenv("MAF_SUBSTRIPS")) ns = std::max(1, std::atoi(e));
-    ensure_strips(h, ns);
-  } else if (!h->strips.empty()) {
-    h->strips_e0 = h->strips_e1 = -1;   // the range changed to one that is assembled in one piece
+    ensure_strips(h, ns);   // (kept across device-only calls in between; rebuilt when the element range changes)
   }
   const bool graphable = h->use_graph && !h->strip && s == h->stream && d_r == h->d_r && d_nz == h->d_nz &&
                          d_xms == h->d_xms && d_cps == h->d_cps && (d_rn == nullptr || d_rn == h->d_rn) &&
