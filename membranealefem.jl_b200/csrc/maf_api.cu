@@ -480,6 +480,7 @@ struct maf_handle {
   // small meshes: the launch sequence of an assembly, captured once per key and replayed (do_assemble_device)
   struct Band { int64_t e0, e1; int32_t* d_order; };   // deterministic path: bands of element rows (ensure_stage)
   std::vector<Band> bands;
+  int64_t n_pair_classes = 0;   // node-pair contribution classes of the deterministic gather (0: not built)
   std::vector<cudaEvent_t> band_staged, band_gathered;   // one pair per band (ordering only, no timing)
   cudaStream_t gather_stream = nullptr;                  // high priority: a band's gather runs beside the next band
   int64_t band_rows = 0, band_e0 = -1, band_e1 = -1;
@@ -627,6 +628,15 @@ static void ensure_gather(maf_handle* h) {
   h->G.n2e_loc = upload(h, S.n2e_loc.data(), S.n2e_loc.size());
   h->G.ij_of = upload(h, GH.ij_of.data(), GH.ij_of.size());
   fill_gather_tables(GH, h->G);
+  build_pair_classes(M, GH);
+  if (!GH.pclass.empty()) {
+    h->G.pclass = upload(h, GH.pclass.data(), GH.pclass.size());
+    h->G.eref = upload(h, GH.eref.data(), GH.eref.size());
+    h->G.ccnt = upload(h, GH.ccnt.data(), GH.ccnt.size());
+    h->G.cde = upload(h, GH.cde.data(), GH.cde.size());
+    h->G.crow = upload(h, GH.crow.data(), GH.crow.size());
+  }
+  h->n_pair_classes = (int64_t)GH.ccnt.size();
   if (GH.nij > MAF_MAX_NIJ) throw std::runtime_error("too many dof-block classes for the gather kernel");
   h->G.npairs = S.npairs;
   h->gather_ready = true;

@@ -19,6 +19,16 @@ struct GatherTables {
   int sym_fill;              // pattern holds rows without a class (MAF_PATTERN_SYM): they are written as zeros
   int ncls;                  // number of classes (the staging rows are padded to an even stride nij >= ncls)
   int64_t npairs;
+  // Which staged rows a node pair sums, precomputed (maf_host.h::build_pair_classes): pair p = (A, B) takes, in
+  // ascending element id, row crow[9 c + q] of element eref[B] + cde[9 c + q], q < ccnt[c], c = pclass[p]. Pairs with
+  // the same relative element offsets and local indices share a class (a few hundred on a structured patch). Without
+  // it (pclass == NULL) the kernel scans the elements of B and looks A up in each: 99 index loads per pair against 27
+  // loads of staged data, the bulk of the gather's time.
+  const uint16_t* pclass;    // npairs, or NULL
+  const int32_t* eref;       // numnp: first element of the node's element list
+  const uint8_t* ccnt;       // classes
+  const int32_t* cde;        // classes x 9
+  const uint8_t* crow;       // classes x 9: 9 a + b
   int64_t ring;              // staging rows live in a ring of this many elements (bands of element rows are staged
                              // and gathered one after the other); 0: one row block per element of the range
 };
@@ -46,15 +56,28 @@ MAF_HD void gather_K_pair(int64_t p, int s, const Config& cfg, const Tables& T, 
 #pragma unroll
   for (int c = 0; c < 2 * NQ; ++c) acc[c] = 0.0;
   // elements that contain both nodes, in ascending element id
-  for (int64_t q = G.n2e_ptr[B]; q < G.n2e_ptr[B + 1]; ++q) {
-    const int64_t e = G.n2e[q];
-    if (e < e0 || e >= e1) continue;
-    int a = -1;
+  const bool tab = G.pclass != nullptr;
+  const int cls9 = tab ? 9 * (int)G.pclass[p] : 0;
+  const int64_t q0 = tab ? 0 : G.n2e_ptr[B], q1 = tab ? (int64_t)G.ccnt[cls9 / 9] : G.n2e_ptr[B + 1];
+  const int64_t er = tab ? (int64_t)G.eref[B] : 0;
+  for (int64_t q = q0; q < q1; ++q) {
+    int64_t e;
+    int rowid;
+    if (tab) {
+      e = er + G.cde[cls9 + q];
+      if (e < e0 || e >= e1) continue;
+      rowid = G.crow[cls9 + q];
+    } else {
+      e = G.n2e[q];
+      if (e < e0 || e >= e1) continue;
+      int a = -1;
 #pragma unroll
-    for (int k = 0; k < 9; ++k)
-      if (T.IX[9 * e + k] == A) a = k;
-    if (a < 0) continue;
-    const double* row = kel + ((size_t)81 * stage_index(e - e0, G.ring) + 9 * a + G.n2e_loc[q]) * nij;
+      for (int k = 0; k < 9; ++k)
+        if (T.IX[9 * e + k] == A) a = k;
+      if (a < 0) continue;
+      rowid = 9 * a + G.n2e_loc[q];
+    }
+    const double* row = kel + ((size_t)81 * stage_index(e - e0, G.ring) + rowid) * nij;
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
       const int c = 2 * (s + L * k);   // a padding entry is read but never written back
@@ -73,7 +96,7 @@ MAF_HD void gather_K_pair(int64_t p, int s, const Config& cfg, const Tables& T, 
       if (c >= G.ncls) continue;
       const int I = G.class_I[c], J = G.class_J[c];
       if (!((mB >> J) & 1u) || !((mA >> I) & 1u)) continue;
-      const int64_t colbase = T.colptr[T.ID[(int64_t)ndf * B + J]] + T.pairoff[p * 8 + J];
+      const int64_t colbase = T.nodecol[8 * (int64_t)B + J] + T.pairoff[p * 8 + J];   // colptr[ID[J, B]]
       nzval[colbase + popc8(mA & cfg.rowmask[J] & ((1u << I) - 1u))] = acc[2 * k + h];
     }
   // P_sym pattern: rows of dof blocks that are identically zero are part of the pattern but own no class

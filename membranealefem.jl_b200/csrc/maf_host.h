@@ -2,6 +2,9 @@
 // (0-based int32 index tables, kernel configuration, symbolic pattern, Dohrmann-Bochev matrices, boundary lists).
 // Pure C++; used by the library (which uploads the result) and by the CPU emulation harness in tests/.
 #pragma once
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
 #include <cmath>
 #include <cstdint>
 #include <stdexcept>
@@ -187,7 +190,89 @@ struct GatherHost {
   int nij = 0;    // stride of a staging row in doubles: the class count rounded up to even (16-byte loads in the gather)
   int ncls = 0;   // number of (row dof, col dof) classes
   int sym_fill = 0;
+  // pair-contribution classes (GatherTables::pclass ...); pclass empty = not built (more than 65535 classes)
+  std::vector<uint16_t> pclass;
+  std::vector<int32_t> eref, cde;
+  std::vector<uint8_t> ccnt, crow;
 };
+// For every node pair (A, B) the staged rows it sums: (element - eref[B], 9 a + b) for the elements that contain both,
+// ascending. Equal lists share a class.
+inline void build_pair_classes(const HostModel& M, GatherHost& GH) {
+  const Symbolic& S = M.sym;
+  struct Sig { uint8_t n; int32_t de[9]; uint8_t row[9]; };
+  auto sig_of = [&](int64_t p, int64_t B, Sig& g) -> bool {
+    const int32_t A = S.nbr[p];
+    const int64_t qa = S.n2e_ptr[B], qb = S.n2e_ptr[B + 1];
+    const int64_t er = qb > qa ? S.n2e[qa] : 0;
+    g.n = 0;
+    for (int k = 0; k < 9; ++k) { g.de[k] = 0; g.row[k] = 0; }
+    for (int64_t q = qa; q < qb; ++q) {
+      const int64_t e = S.n2e[q];
+      int a = -1;
+      for (int k = 0; k < 9; ++k)
+        if (M.IX0[9 * e + k] == A) a = k;
+      if (a < 0) continue;
+      if (g.n >= 9) return false;   // (not a 9-node tensor-product mesh: the caller gives the classes up)
+      g.de[g.n] = (int32_t)(e - er);
+      g.row[g.n] = (uint8_t)(9 * a + S.n2e_loc[q]);
+      g.n += 1;
+    }
+    return true;
+  };
+  auto hash_of = [](const Sig& g) {
+    uint64_t h = 1469598103934665603ull ^ g.n;
+    for (int k = 0; k < 9; ++k) {
+      h = (h ^ (uint32_t)g.de[k]) * 1099511628211ull;
+      h = (h ^ g.row[k]) * 1099511628211ull;
+    }
+    return h;
+  };
+  auto same = [](const Sig& x, const Sig& y) {
+    if (x.n != y.n) return false;
+    for (int k = 0; k < 9; ++k)
+      if (x.de[k] != y.de[k] || x.row[k] != y.row[k]) return false;
+    return true;
+  };
+  GH.eref.assign(M.numnp, 0);
+  for (int64_t B = 0; B < M.numnp; ++B)
+    if (S.n2e_ptr[B + 1] > S.n2e_ptr[B]) GH.eref[B] = S.n2e[S.n2e_ptr[B]];
+  std::vector<uint64_t> hp(S.npairs);
+  std::mutex mu;
+  std::unordered_map<uint64_t, Sig> reps;   // one representative list per hash
+  std::atomic<bool> collision{false};
+  parallel_for(M.numnp, [&](int64_t lo, int64_t hi) {
+    std::unordered_map<uint64_t, Sig> local;
+    Sig g;
+    for (int64_t B = lo; B < hi; ++B)
+      for (int64_t p = S.nbr_ptr[B]; p < S.nbr_ptr[B + 1]; ++p) {
+        if (!sig_of(p, B, g)) collision = true;
+        const uint64_t h = hash_of(g);
+        hp[p] = h;
+        auto it = local.find(h);
+        if (it == local.end()) local.emplace(h, g);
+        else if (!same(it->second, g)) collision = true;
+      }
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& kv : local) {
+      auto it = reps.find(kv.first);
+      if (it == reps.end()) reps.emplace(kv.first, kv.second);
+      else if (!same(it->second, kv.second)) collision = true;
+    }
+  });
+  GH.pclass.clear();
+  GH.ccnt.clear(); GH.cde.clear(); GH.crow.clear();
+  if (collision || reps.size() > 65535) return;   // the gather kernel falls back to scanning the element lists
+  std::unordered_map<uint64_t, uint16_t> id;
+  for (auto& kv : reps) {
+    id.emplace(kv.first, (uint16_t)GH.ccnt.size());
+    GH.ccnt.push_back(kv.second.n);
+    for (int k = 0; k < 9; ++k) { GH.cde.push_back(kv.second.de[k]); GH.crow.push_back(kv.second.row[k]); }
+  }
+  GH.pclass.resize(S.npairs);
+  parallel_for(S.npairs, [&](int64_t lo, int64_t hi) {
+    for (int64_t p = lo; p < hi; ++p) GH.pclass[p] = id.find(hp[p])->second;
+  });
+}
 inline void build_gather_host(const HostModel& M, GatherHost& GH) {
   const Symbolic& S = M.sym;
   GH.pair_node.resize(S.npairs);
@@ -214,6 +299,7 @@ inline void fill_gather_tables(const GatherHost& GH, GatherTables& G) {
   G.sym_fill = GH.sym_fill;
   G.ncls = GH.ncls;
   G.ring = 0;
+  G.pclass = nullptr; G.eref = nullptr; G.ccnt = nullptr; G.cde = nullptr; G.crow = nullptr;
 }
 
 // ---- strips of element rows over several GPUs (the reference's per-task chunks, FiniteElement.jl:88-89) ----

@@ -200,8 +200,20 @@ int emu_assemble(void* h, const double* xms, const double* cps, double time, dou
       G.n2e_ptr = M.sym.n2e_ptr.data(); G.n2e = M.sym.n2e.data(); G.n2e_loc = M.sym.n2e_loc.data();
       G.ij_of = GH.ij_of.data(); G.npairs = M.sym.npairs;
       fill_gather_tables(GH, G);
+      // the product gathers through the precomputed pair-contribution classes: the emulation does both and insists
+      // on identical sums (the scan over the element lists is the definition, the table the fast form)
+      std::vector<double> nz_scan(nzval, nzval + M.sym.nnz);
+      for (int64_t p = 0; p < G.npairs; ++p)
+        for (int s = 0; s < MAF_GATHER_LANES; ++s)
+          gather_K_pair(p, s, M.cfg, T, G, kel.data(), GH.nij, e0, e1, nz_scan.data());
+      build_pair_classes(M, GH);
+      if (GH.pclass.empty()) throw std::runtime_error("emulation: pair-contribution classes were not built");
+      G.pclass = GH.pclass.data(); G.eref = GH.eref.data(); G.ccnt = GH.ccnt.data(); G.cde = GH.cde.data();
+      G.crow = GH.crow.data();
       for (int64_t p = 0; p < G.npairs; ++p)
         for (int s = 0; s < MAF_GATHER_LANES; ++s) gather_K_pair(p, s, M.cfg, T, G, kel.data(), GH.nij, e0, e1, nzval);
+      if (std::memcmp(nz_scan.data(), nzval, sizeof(double) * (size_t)M.sym.nnz) != 0)
+        throw std::runtime_error("emulation: gather through the pair classes differs from the scan");
       for (int64_t k = 0; k < M.numnp * M.ndf; ++k) gather_r_row(k, M.cfg, T, G, rel.data(), e0, e1, r);
     }
     std::vector<double> sm(B_DOUBLES);
