@@ -96,7 +96,7 @@ MAF_HD void gather_K_pair(int64_t p, int s, const Config& cfg, const Tables& T, 
       if (c >= G.ncls) continue;
       const int I = G.class_I[c], J = G.class_J[c];
       if (!((mB >> J) & 1u) || !((mA >> I) & 1u)) continue;
-      const int64_t colbase = T.nodecol[8 * (int64_t)B + J] + T.pairoff[p * 8 + J];   // colptr[ID[J, B]]
+      const int64_t colbase = T.colptr[T.ID[(int64_t)ndf * B + J]] + T.pairoff[p * 8 + J];
       nzval[colbase + popc8(mA & cfg.rowmask[J] & ((1u << I) - 1u))] = acc[2 * k + h];
     }
   // P_sym pattern: rows of dof blocks that are identically zero are part of the pattern but own no class
