@@ -157,7 +157,7 @@ int maf_area_kernel_times(maf_handle* h, double* out_ms, int64_t n);
  * out[6] assemblies replayed from a captured CUDA graph so far (meshes of <= 16384 elements assembling into the
  * handle's own buffers: their ~10 launches are bound by the host's launch rate; MAF_NO_GRAPH=1 disables it),
  * out[7] bytes of staging memory the deterministic path holds (0 until it ran), out[8] its band height in element
- * rows (0 = the whole range staged at once; large ranges are staged in a ring of three bands, ~8 % of nzval;
+ * rows (0 = the whole range staged at once; large ranges are staged in a ring of three bands, <= 10 % of nzval;
  * MAF_BAND_ROWS overrides the height). */
 int maf_kernel_info(maf_handle* h, int64_t* out9);
 
