@@ -628,7 +628,10 @@ static void ensure_gather(maf_handle* h) {
   h->G.n2e_loc = upload(h, S.n2e_loc.data(), S.n2e_loc.size());
   h->G.ij_of = upload(h, GH.ij_of.data(), GH.ij_of.size());
   fill_gather_tables(GH, h->G);
-  build_pair_classes(M, GH);
+  // (MAF_NO_PAIR_CLASSES=1: keep the scanning gather -- the fallback for meshes with more than 65535 classes; tests
+  // compare the two on the device)
+  const char* no_pc = std::getenv("MAF_NO_PAIR_CLASSES");
+  if (!(no_pc && *no_pc == '1')) build_pair_classes(M, GH);
   if (!GH.pclass.empty()) {
     h->G.pclass = upload(h, GH.pclass.data(), GH.pclass.size());
     h->G.eref = upload(h, GH.eref.data(), GH.eref.size());

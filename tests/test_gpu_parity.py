@@ -400,3 +400,20 @@ def test_banded_deterministic_staging(monkeypatch, name, rows):
     assert band.launch_count() > ref.launch_count() + 4        # the bands did run
     ref.close()
     band.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["alevb_pull_17x17", "lag_pull_flat_7x7", "alev_bend_4x4_pn"])
+def test_gather_through_pair_classes_equals_the_scanning_gather(monkeypatch, name):
+    """The deterministic gather looks the staged rows of a node pair up in precomputed contribution classes; the
+    scanning form (element lists of the column node, row node searched in each: the definition, and the fallback for
+    meshes with more than 65535 classes) must give the same bits."""
+    p, hm, om, xms, cps, time, dt, args = make_case(name)
+    fast = maf.Assembler(hm, p)
+    r0, k0, n0 = fast.assemble(xms, cps, time, dt, scatter_mode=maf.SCATTER_DETERMINISTIC)
+    monkeypatch.setenv("MAF_NO_PAIR_CLASSES", "1")
+    scan = maf.Assembler(hm, p)
+    r1, k1, n1 = scan.assemble(xms, cps, time, dt, scatter_mode=maf.SCATTER_DETERMINISTIC)
+    assert np.array_equal(r0, r1) and np.array_equal(k0, k1) and n0 == n1
+    fast.close()
+    scan.close()
